@@ -1,0 +1,338 @@
+/*
+ * adgs_b200.h -- C ABI of the B200-native AD-GS hot path (libadgs_b200.so).
+ *
+ * Plain pointers and sizes only; no torch / C++ types cross this boundary. Every DEVICE pointer
+ * must be valid on the current CUDA device, every launch goes to the `stream` argument (the
+ * host passes torch's current stream), and no entry point allocates device memory: the caller
+ * owns all storage (directly, or through the adgs_alloc_fn callbacks that mirror the
+ * reference's std::function<char*(size_t)> arena allocators).
+ *
+ * Each entry point names the reference interface it replaces; paths are relative to the
+ * reference checkout, RZ/ = submodules/depth-diff-gaussian-rasterization/,
+ * KNN/ = submodules/simple-knn/.
+ *
+ * Return value: >= 0 on success (adgs_rasterize_forward returns num_rendered), < 0 = adgs_status.
+ */
+#ifndef ADGS_B200_H_INCLUDED
+#define ADGS_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADGS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ADGS_API __attribute__((visibility("default")))
+#else
+#define ADGS_API
+#endif
+
+typedef struct CUstream_st* adgs_stream_t;
+
+/* Arena allocator: must return a DEVICE pointer to at least `bytes` bytes, 128-byte aligned.
+ * Replaces the three std::function<char*(size_t)> of RZ/cuda_rasterizer/rasterizer.h:34-36
+ * (bound to torch tensors by resizeFunctional, RZ/rasterize_points.cu:27-33). */
+typedef char* (*adgs_alloc_fn)(size_t bytes, void* user);
+
+typedef enum adgs_status {
+    ADGS_OK = 0,
+    ADGS_ERR_ARG = -1,         /* bad argument (null pointer, bad shape) */
+    ADGS_ERR_CUDA = -2,        /* a CUDA call failed; adgs_last_cuda_error() has the text */
+    ADGS_ERR_CAPACITY = -3,    /* binning arena too small in the *_async path */
+    ADGS_ERR_UNSUPPORTED = -4, /* e.g. D_S > 32, SH degree > 3 (same limits as the reference) */
+    ADGS_ERR_ALLOC = -5        /* an adgs_alloc_fn returned null */
+} adgs_status;
+
+#define ADGS_MAX_SEMANTIC 32 /* RZ/cuda_rasterizer/config.h:18 */
+#define ADGS_TILE 16         /* RZ/cuda_rasterizer/config.h:16-17 */
+
+ADGS_API int adgs_abi_version(void);
+ADGS_API const char* adgs_status_string(int status);
+ADGS_API const char* adgs_last_cuda_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Camera / raster settings: the fields of GaussianRasterizationSettings
+ * (RZ/diff_gaussian_rasterization/__init__.py:176-189). Matrices are the 16 floats of the
+ * torch tensors as they lie in memory, i.e. the transposed W2C / full projection of
+ * scene/cameras.py:77-79, read as m[col*4+row] (RZ/cuda_rasterizer/auxiliary.h:58-77).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct adgs_camera {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    float scale_modifier;
+    int32_t sh_degree;
+    int32_t prefiltered;
+    int32_t inv_depth;
+    int32_t debug;           /* !=0: synchronise + check after every stage (CHECK_CUDA, auxiliary.h:166) */
+    int32_t _pad;
+    const float* bg;         /* device, 3 */
+    const float* viewmatrix; /* device, 16 */
+    const float* projmatrix; /* device, 16 */
+    const float* campos;     /* device, 3 */
+} adgs_camera;
+
+/* Per-Gaussian inputs of CudaRasterizer::Rasterizer::forward (RZ/cuda_rasterizer/rasterizer.h:33-65).
+ * A null pointer means "not provided" exactly like the reference's empty-tensor sentinel
+ * (RZ/diff_gaussian_rasterization/__init__.py:220-236). */
+typedef struct adgs_gaussians {
+    int32_t P;                /* number of Gaussians */
+    int32_t M;                /* SH coefficients per Gaussian as laid out in `shs` (0 if none) */
+    int32_t D_S;              /* semantic channels (0 if none), <= 32 */
+    int32_t _pad;
+    const float* means3D;     /* (P,3) */
+    const float* shs;         /* (P,M,3) or null */
+    const float* colors_precomp; /* (P,3) or null */
+    const float* flow_points; /* (P,3) or null */
+    const float* semantic;    /* (P,D_S) or null */
+    const float* opacities;   /* (P,1) */
+    const float* scales;      /* (P,3) or null */
+    const float* rotations;   /* (P,4) wxyz, NOT normalised by the rasterizer (forward.cu:127) */
+    const float* cov3D_precomp; /* (P,6) or null */
+} adgs_gaussians;
+
+/* Outputs of the forward: the six tensors of _RasterizeGaussians.forward
+ * (RZ/diff_gaussian_rasterization/__init__.py:107), planar CHW float32. The library
+ * writes every element (no pre-zeroing needed). */
+typedef struct adgs_images {
+    float* color;    /* (3,H,W) */
+    float* depth;    /* (1,H,W) */
+    float* opacity;  /* (1,H,W)  = 1 - T_final */
+    float* flow;     /* (3,H,W) */
+    float* semantic; /* (D_S,H,W) */
+    int32_t* radii;  /* (P,) */
+} adgs_images;
+
+/* Arena sizes. Layout is a pure function of (P), (R), (W,H) so the backward can re-derive it
+ * from the same base pointers (same contract as RZ/cuda_rasterizer/rasterizer_impl.cu:398-400). */
+ADGS_API size_t adgs_geometry_bytes(int32_t P);
+ADGS_API size_t adgs_binning_bytes(int64_t R);
+ADGS_API size_t adgs_image_bytes(int32_t width, int32_t height);
+ADGS_API size_t adgs_backward_scratch_bytes(int32_t P);
+
+/* Replaces CudaRasterizer::Rasterizer::markVisible (rasterizer.h:24-29; _C.mark_visible). */
+ADGS_API int adgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                      const float* projmatrix, uint8_t* present, adgs_stream_t stream);
+
+/* Replaces CudaRasterizer::Rasterizer::forward (rasterizer.h:31-65; _C.rasterize_gaussians,
+ * RZ/rasterize_points.cu:35-140). Returns num_rendered (>= 0). Like the reference it performs
+ * exactly one blocking 4-byte device-to-host read (rasterizer_impl.cu:288) to size the
+ * binning arena. */
+ADGS_API int adgs_rasterize_forward(const adgs_camera* cam, const adgs_gaussians* g, const adgs_images* out,
+                           adgs_alloc_fn geometry_alloc, adgs_alloc_fn binning_alloc,
+                           adgs_alloc_fn image_alloc, void* alloc_user, adgs_stream_t stream);
+
+/* Same computation with caller-provided arenas and NO host synchronisation: `binning` must hold
+ * adgs_binning_bytes(capacity) bytes. The number of rendered instances stays on the device
+ * (adgs_geometry_layout.num_rendered); if it exceeds `capacity` the overflow flag is raised and
+ * the images are undefined -- the caller checks adgs_read_counters() later and retries bigger. */
+ADGS_API int adgs_rasterize_forward_async(const adgs_camera* cam, const adgs_gaussians* g, const adgs_images* out,
+                                 char* geometry, char* binning, int64_t capacity, char* image,
+                                 adgs_stream_t stream);
+
+/* Async 8-byte copy of {num_rendered, overflow} from the geometry arena into pinned host memory. */
+ADGS_API int adgs_read_counters(const char* geometry, int32_t P, uint32_t* host_pinned_2, adgs_stream_t stream);
+
+/* Cotangents of the five images (grad_radii is ignored, as in the reference). Null = zero. */
+typedef struct adgs_image_grads {
+    const float* dL_dcolor;    /* (3,H,W) */
+    const float* dL_ddepth;    /* (1,H,W) */
+    const float* dL_dflow;     /* (3,H,W) */
+    const float* dL_dsemantic; /* (D_S,H,W) */
+    const float* dL_dopacity;  /* (1,H,W) grad_img_opacity */
+} adgs_image_grads;
+
+/* The ten gradients of _C.rasterize_gaussians_backward (RZ/rasterize_points.cu:253). The library
+ * writes every element of every non-null tensor (zeros for culled Gaussians): no pre-zeroing. */
+typedef struct adgs_gaussian_grads {
+    float* dL_dmeans2D;     /* (P,3), z unused (=0) */
+    float* dL_dcolors;      /* (P,3) */
+    float* dL_dopacity;     /* (P,1) */
+    float* dL_dmeans3D;     /* (P,3) */
+    float* dL_dcov3D;       /* (P,6) */
+    float* dL_dsh;          /* (P,M,3) */
+    float* dL_dscales;      /* (P,3) */
+    float* dL_drotations;   /* (P,4) */
+    float* dL_dflow_points; /* (P,3) */
+    float* dL_dsemantic;    /* (P,D_S) */
+} adgs_gaussian_grads;
+
+/* Replaces CudaRasterizer::Rasterizer::backward (rasterizer.h:67-101;
+ * _C.rasterize_gaussians_backward, RZ/rasterize_points.cu:142-254). `img_opacity` is the
+ * forward's opacity image (the reference's final_T buffer, forward.cu:389 / backward.cu:473). */
+ADGS_API int adgs_rasterize_backward(const adgs_camera* cam, const adgs_gaussians* g, const int32_t* radii,
+                            const char* geometry, int64_t R, const char* binning, const char* image,
+                            const float* img_opacity, const adgs_image_grads* dpix,
+                            const adgs_gaussian_grads* grads, char* scratch, adgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Introspection (tests / parity only): byte offsets of the internal arrays inside the arenas,
+ * the analogue of re-running GeometryState/BinningState/ImageState::fromChunk
+ * (rasterizer_impl.cu:155-194) on a returned buffer.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct adgs_geometry_layout {
+    size_t counters;       /* uint32[4]: num_rendered, overflow, -, -            */
+    size_t depths;         /* uint32 [P]  float bits of view-space z, SORTED ascending (culled = ~0) */
+    size_t tiles_touched;  /* uint32 [P]                                          */
+    size_t record;         /* float  [P][16] packed blend record                  */
+    size_t cov3D;          /* float  [P][6]                                       */
+    size_t clamped;        /* uint8  [P]  bit c set = channel c clamped           */
+    size_t depth_order;    /* uint32 [P]  Gaussian ids sorted by (depth, id)      */
+    size_t point_offsets;  /* uint32 [P]  inclusive scan of tiles_touched in depth order */
+    size_t total;
+} adgs_geometry_layout;
+
+typedef struct adgs_binning_layout {
+    /* The sorted lists live in the primary or the alternate buffers depending on the parity of
+     * the tile-sort pass count, a function of the image size only: adgs_binning_result_in_alt(). */
+    size_t point_list;          /* uint32 [R] Gaussian id per instance, sorted by (tile, depth, id) */
+    size_t point_list_tile;     /* uint32 [R] tile id per sorted instance                           */
+    size_t point_list_alt;
+    size_t point_list_tile_alt;
+    size_t total;
+} adgs_binning_layout;
+
+typedef struct adgs_image_layout {
+    size_t ranges;    /* uint32 [tiles][2] */
+    size_t n_contrib; /* uint32 [H*W]      */
+    size_t total;
+} adgs_image_layout;
+
+ADGS_API int adgs_geometry_offsets(int32_t P, adgs_geometry_layout* out);
+ADGS_API int adgs_binning_offsets(int64_t R, adgs_binning_layout* out);
+ADGS_API int adgs_binning_result_in_alt(int32_t width, int32_t height);
+ADGS_API int adgs_image_offsets(int32_t width, int32_t height, adgs_image_layout* out);
+
+/* Stand-alone stable LSD radix sort of (uint32 key, uint32 value) pairs on key bits
+ * [begin_bit, end_bit) -- the CUB-free onesweep that replaces cub::DeviceRadixSort::SortPairs
+ * (rasterizer_impl.cu:310-315; KNN/simple_knn.cu:210-213). Exposed for tests and for distCUDA2.
+ * Both buffer pairs are clobbered; returns 0 when the sorted pairs are in (keys_out, vals_out),
+ * 1 when they are in (keys_in, vals_in) (even number of 8-bit passes), < 0 on error.
+ * workspace: adgs_sort_workspace_bytes(n). */
+ADGS_API size_t adgs_sort_workspace_bytes(int64_t n);
+ADGS_API int adgs_sort_pairs(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                    int64_t n, int32_t begin_bit, int32_t end_bit, char* workspace,
+                    adgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Trajectory (object-aware B-spline / Fourier / polynomial / cumulative quaternion B-spline)
+ * fused with the rasterizer front end. Replaces, for one time t (and optionally a second time
+ * flow_t), GaussianModel.get_deformed_pkg / get_deformed_xyz (scene/gaussian_model.py:173-231),
+ * get_scaling (:88-91), get_obj_mask (:154-159) and utils/func_utils.py:get_func_result
+ * (:121-173) followed by the per-Gaussian preprocess (forward.cu:155-256).
+ *
+ * The host reduces get_func_result's four linear bases (B-spline window, polynomial, Fourier;
+ * func_utils.py:127-153) to one sparse weight list per attribute: value = sum_j
+ * param[..., col[j]] * w[j]. `w1` carries the weights of the second time (flow_t) over the same
+ * column list so that both evaluations read each coefficient once.
+ * ---------------------------------------------------------------------------------------- */
+#define ADGS_MAX_TERMS 48
+#define ADGS_MAX_QUAT_ORDER 7
+
+typedef struct adgs_lin_basis {
+    int32_t n;                    /* number of terms (0 = attribute not deformed) */
+    int32_t n_cols;               /* C: total parameter columns of the attribute */
+    int16_t col[ADGS_MAX_TERMS];
+    float w0[ADGS_MAX_TERMS];     /* weights at t */
+    float w1[ADGS_MAX_TERMS];     /* weights at flow_t (xyz / background only) */
+} adgs_lin_basis;
+
+typedef struct adgs_quat_basis {
+    int32_t k;                    /* spline order k_q (0 with n_ctrl==0 => no quaternion spline) */
+    int32_t n_ctrl;               /* n_q */
+    int32_t start;                /* first control quaternion of the window (column index) */
+    int32_t _pad;
+    float cum[ADGS_MAX_QUAT_ORDER + 1]; /* cum[i] = sum_{j>=i} B_j(u), i = 1..k (func_utils.py:163) */
+} adgs_quat_basis;
+
+typedef struct adgs_time_basis {
+    adgs_lin_basis xyz;        /* order_args['xyz'] */
+    adgs_lin_basis background; /* order_args['background'] */
+    adgs_lin_basis shs;        /* order_args['shs'] */
+    adgs_lin_basis rotation;   /* linear part of order_args['rotation'] */
+    adgs_quat_basis quat;      /* quaternion-spline part of order_args['rotation'] */
+    float t;                   /* camera time (time mask, gaussian_model.py:207-214) */
+    int32_t use_time_mask;
+    int32_t has_flow;          /* evaluate xyz at the second time too (gaussian_renderer/__init__.py:54-57) */
+    int32_t _pad;
+} adgs_time_basis;
+
+/* Parameter storage of the B200-native model (host container: adgs_b200/gaussian_model.py).
+ * Gaussians are ordered [scene (N_scene) ; object (N_obj)], N = N_scene + N_obj, i.e. the order
+ * of every torch.cat in scene/gaussian_model.py. Per-Gaussian rows stay AoS where a row is one
+ * vector load; the wide per-Gaussian blocks are planar so that a warp reads 128-byte lines:
+ *   xyz (N,3) scaling (N,3) rotation (N,4) opacity (N,)                    raw, pre-activation
+ *   sh4       (12,N,4)   the (16,3) SH block of Gaussian g, flattened, in float4 chunks
+ *   shs_deform4 (ceil(3*Cs/4),N,4)  (3,Cs) block flattened, in float4 chunks
+ *   xyz_deform (Cx,3,N_obj)   rot_deform (Cr,N_obj,4)   background_deform (3,Cb)
+ *   gs_time (N_obj,)  gs_time_sigma (N_obj,2)
+ * The same struct describes the gradient buffers (same layouts). */
+typedef struct adgs_model {
+    int32_t N_scene;
+    int32_t N_obj;
+    float* xyz;
+    float* scaling;
+    float* rotation;
+    float* opacity;
+    float* sh4;
+    float* shs_deform4;
+    float* xyz_deform;
+    float* rot_deform;
+    float* background_deform;
+    float* gs_time;        /* not a trainable parameter in the reference; null in gradient structs */
+    float* gs_time_sigma;
+} adgs_model;
+
+/* Optional materialised outputs of the trajectory (the `deform_pkg` of
+ * gaussian_renderer/__init__.py:61-66 in reference shapes); any pointer may be null. */
+typedef struct adgs_deformed {
+    float* xyz;      /* (N,3) */
+    float* rotation; /* (N,4) normalised */
+    float* shs;      /* (N,16,3) */
+    float* opacity;  /* (N,1) */
+    float* scaling;  /* (N,3) exp-activated */
+    float* flow_xyz; /* (N,3) xyz at flow_t */
+} adgs_deformed;
+
+/* get_deformed_pkg(t) alone (no rasterisation): fills `out`. */
+ADGS_API int adgs_trajectory_forward(const adgs_model* model, const adgs_time_basis* basis,
+                            const adgs_deformed* out, adgs_stream_t stream);
+
+/* Fused render forward: trajectory + preprocess + binning + blend, no host synchronisation.
+ * semantic = object mask (render_objmask=True, gaussian_renderer/__init__.py:71-73) when
+ * `render_objmask` != 0. Arenas as in adgs_rasterize_forward_async. `saved` (N*8 floats) keeps
+ * what the backward needs from the trajectory (xyz(t), activated opacity, ...). */
+ADGS_API size_t adgs_render_saved_bytes(int32_t N);
+ADGS_API int adgs_render_forward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
+                        int32_t render_objmask, const adgs_images* out, const adgs_deformed* deformed,
+                        char* geometry, char* binning, int64_t capacity, char* image, char* saved,
+                        adgs_stream_t stream);
+
+/* Fused render backward: blend backward + preprocess backward + trajectory backward, writing
+ * DENSE parameter gradients in the model layouts (zeros outside the B-spline windows, which is
+ * what autograd produces in the reference -- SURVEY section 7 hard part 6) and the screen-space
+ * gradient dL_dmeans2D (N,3) used by densification (gaussian_model.py:863-867). */
+ADGS_API int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
+                         int32_t render_objmask, const int32_t* radii, const char* geometry,
+                         const char* binning, const char* image, const char* saved,
+                         const float* img_opacity, const adgs_image_grads* dpix,
+                         const adgs_model* grads, float* dL_dmeans2D, char* scratch,
+                         adgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * simple-knn: replaces SimpleKNN::knn / distCUDA2 (KNN/simple_knn.h:18, KNN/spatial.cu:16-26):
+ * mean squared distance to the 3 nearest neighbours of every point.
+ * ---------------------------------------------------------------------------------------- */
+ADGS_API size_t adgs_knn_workspace_bytes(int32_t P);
+ADGS_API int adgs_dist_cuda2(int32_t P, const float* points, float* mean_dist2, char* workspace,
+                    adgs_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADGS_B200_H_INCLUDED */
