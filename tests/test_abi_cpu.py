@@ -1,0 +1,66 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/adgs_b200.h declares
+(no compute calls), and the host-visible sizing functions behave."""
+import ctypes as C
+import os
+import re
+
+from adgs_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "adgs_b200.h")).read()
+    return sorted(set(re.findall(r"ADGS_API[^;(]*?\b(adgs_\w+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = L.load()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/adgs_b200.h but not exported"
+        assert n in L.SIGNATURES, f"{n} has no ctypes signature in adgs_b200/_lib.py"
+    assert sorted(L.SIGNATURES) == names
+
+
+def test_version_and_status_strings():
+    lib = L.load()
+    assert lib.adgs_abi_version() == 1
+    assert lib.adgs_status_string(0) == b"ok"
+    assert b"argument" in lib.adgs_status_string(-1)
+
+
+def test_arena_sizes_are_deterministic_and_monotone():
+    lib = L.load()
+    assert lib.adgs_geometry_bytes(1000) == lib.adgs_geometry_bytes(1000)
+    assert lib.adgs_geometry_bytes(2000) > lib.adgs_geometry_bytes(1000) > 0
+    assert lib.adgs_binning_bytes(10) < lib.adgs_binning_bytes(10_000_000)
+    assert lib.adgs_image_bytes(1242, 375) >= 1242 * 375 * 4
+    gl = L.GeometryLayout()
+    assert lib.adgs_geometry_offsets(12345, C.byref(gl)) == 0
+    offs = [gl.counters, gl.depths, gl.tiles_touched, gl.record, gl.cov3D, gl.clamped]
+    assert offs == sorted(offs) and all(o % 128 == 0 for o in offs)
+    assert gl.total + 128 <= lib.adgs_geometry_bytes(12345)
+    # per-Gaussian forward state stays ~120 B (vs 79 B + CUB temp in the reference, rasterizer_impl.cu:155-170)
+    assert lib.adgs_geometry_bytes(1_000_000) < 140 * 1_000_000
+    # 16 B per instance (two uint32 ping-pong pairs) vs the reference's 24 B + CUB temp (rasterizer_impl.cu:180-194)
+    assert lib.adgs_binning_bytes(3_000_000) < 20 * 3_000_000
+
+
+def test_struct_sizes_match_header():
+    # LP64 layout of the structs that cross the boundary
+    assert C.sizeof(L.Camera) == 72
+    assert C.sizeof(L.Gaussians) == 16 + 9 * 8
+    assert C.sizeof(L.Images) == 48
+    assert C.sizeof(L.LinBasis) == 8 + 96 + 192 + 192
+    assert C.sizeof(L.QuatBasis) == 16 + 32
+    assert C.sizeof(L.TimeBasis) == 4 * 488 + 48 + 16
+    assert C.sizeof(L.Model) == 8 + 11 * 8
+
+
+def test_bad_arguments_are_rejected_without_a_gpu():
+    lib = L.load()
+    assert lib.adgs_mark_visible(-1, None, None, None, None, None) == -1
+    assert lib.adgs_sort_pairs(None, None, None, None, 10, 0, 40, None, None) == -1
+    assert lib.adgs_rasterize_backward(None, None, None, None, 0, None, None, None, None, None, None, None) == -1
