@@ -209,10 +209,12 @@ SIGNATURES = {
     "adgs_trajectory_forward": (C.c_int, [_P(Model), _P(TimeBasis), _P(Deformed), C.c_void_p]),
     "adgs_render_saved_bytes": (C.c_size_t, [C.c_int32]),
     "adgs_render_forward": (C.c_int, [_P(Camera), _P(Model), _P(TimeBasis), C.c_int32, _P(Images), _P(Deformed),
-                                      C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                      C.c_void_p, C.c_void_p, C.c_int64, ALLOC_FN, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "adgs_render_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "adgs_render_backward": (C.c_int, [_P(Camera), _P(Model), _P(TimeBasis), C.c_int32, C.c_void_p, C.c_void_p,
-                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _P(ImageGrads), _P(Model),
-                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, _P(ImageGrads),
+                                       _P(Model), C.c_void_p, C.c_void_p, C.c_void_p]),
     "adgs_knn_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "adgs_dist_cuda2": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

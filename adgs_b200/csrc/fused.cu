@@ -1,0 +1,711 @@
+// Fused trajectory + projection kernels over the planar model storage (adgs_model), their
+// backward, and the C-ABI entry points adgs_trajectory_forward / adgs_render_forward /
+// adgs_render_backward.
+//
+// One thread per Gaussian. Forward reads every parameter once -- coalesced: AoS rows that are a
+// single vector (xyz, scale, quaternion), float4 planes for the wide blocks (SH, SH-deform,
+// control quaternions), scalar planes for the position control points -- evaluates
+//   position  = xyz + sum_j xyz_deform[col_j] w_j (+ the same columns with the flow-time weights)
+//               + background(t)                                  (gaussian_model.py:173-185)
+//   rotation  = normalize(scene quaternion | cumulative quaternion B-spline)   (:187-196)
+//   SH DC    += sum_j shs_deform[col_j] w_j                       (:198-205)
+//   opacity   = sigmoid(o) * exp(-0.5 ((t - tau)/sigma_+-)^2)      (:207-214)
+//   scale     = exp(s)                                            (:88-91)
+// and runs the per-Gaussian rasterizer front end (forward.cu:155-256) in the same registers, so
+// the deformed tensors never round-trip HBM. 48 bytes per Gaussian are kept for the backward.
+#include "api_internal.cuh"
+#include "trajectory.cuh"
+
+namespace adgs {
+namespace {
+
+constexpr int kSavedFloats = 12;  // xyz_t(3) op_act(1) | q(4) | dc_t(3) pad(1)
+
+struct FusedFwdArgs {
+    adgs_model m;
+    adgs_time_basis tb;
+    adgs_deformed out;  // optional materialised tensors
+    int render;         // 0: trajectory only
+    int render_objmask;
+    RasterParams rp;
+    const float* view;
+    const float* proj;
+    const float* campos;
+    int32_t* radii;
+    uint32_t* depth_keys;
+    uint32_t* tiles_touched;
+    float4* record;
+    float* cov3D;
+    uint8_t* clamped;
+    float4* saved;
+};
+
+__device__ __forceinline__ void lin_eval3_planar(const float* base, int n_obj, int j, const adgs_lin_basis& b,
+                                                 float* v0, float* v1, bool second)
+{
+    // base: (C,3,n_obj); value_d += p[col][d][j] * w
+    for (int t = 0; t < b.n; ++t) {
+        const float* p = base + ((size_t)b.col[t] * 3) * n_obj + j;
+        const float w0 = b.w0[t];
+        const float w1 = b.w1[t];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float x = __ldg(p + (size_t)d * n_obj);
+            v0[d] += x * w0;
+            if (second) v1[d] += x * w1;
+        }
+    }
+}
+
+// Object rotation before the final normalisation: [static quaternion if no spline] + linear terms
+// + quaternion spline, in wxyz.
+__device__ __forceinline__ float4 object_rotation_raw(const adgs_model& m, const adgs_time_basis& tb, int g, int j,
+                                                      Quat* qt_out, float* norms_out)
+{
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* rd = reinterpret_cast<const float4*>(m.rot_deform);
+    if (tb.quat.n_ctrl == 0) q = reinterpret_cast<const float4*>(m.rotation)[g];
+    for (int t = 0; t < tb.rotation.n; ++t) {
+        const float4 p = __ldg(rd + (size_t)tb.rotation.col[t] * m.N_obj + j);
+        const float w = tb.rotation.w0[t];
+        q.x += p.x * w;
+        q.y += p.y * w;
+        q.z += p.z * w;
+        q.w += p.w * w;
+    }
+    if (tb.quat.n_ctrl != 0) {
+        Quat qt[ADGS_MAX_QUAT_ORDER + 1];
+        const int k = tb.quat.k;
+#pragma unroll
+        for (int i = 0; i <= ADGS_MAX_QUAT_ORDER; ++i) {
+            float nrm = 1.f;
+            if (i <= k) {
+                const float4 p = __ldg(rd + (size_t)(tb.quat.start + i) * m.N_obj + j);
+                qt[i] = ctrl_quat(p, nrm);
+            } else {
+                qt[i] = Quat{0.f, 0.f, 0.f, 1.f};
+            }
+            if (qt_out) {
+                qt_out[i] = qt[i];
+                norms_out[i] = nrm;
+            }
+        }
+        const Quat r = quat_spline(qt, k, tb.quat.cum);
+        q.x += r.w;
+        q.y += r.x;
+        q.z += r.y;
+        q.w += r.z;
+    }
+    return q;
+}
+
+__global__ void __launch_bounds__(256) fused_forward_kernel(const __grid_constant__ FusedFwdArgs a)
+{
+    __shared__ CamSmem cam;
+    __shared__ float s_bg[6];
+    const adgs_model& m = a.m;
+    const adgs_time_basis& tb = a.tb;
+    const int N = m.N_scene + m.N_obj;
+    if (threadIdx.x < 6) {
+        const int d = threadIdx.x % 3;
+        const bool second = threadIdx.x >= 3;
+        float v = 0.f;
+        for (int t = 0; t < tb.background.n; ++t)
+            v += m.background_deform[d * tb.background.n_cols + tb.background.col[t]] *
+                 (second ? tb.background.w1[t] : tb.background.w0[t]);
+        s_bg[threadIdx.x] = v;
+    }
+    if (a.render) {
+        load_camera(cam, a.view, a.proj, a.campos, nullptr);
+    } else {
+        __syncthreads();
+    }
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+    const bool is_obj = g >= m.N_scene;
+    const int j = g - m.N_scene;
+    const bool flow = tb.has_flow != 0;
+
+    // ---- position ------------------------------------------------------------------------
+    float xt[3], xf[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) xt[d] = xf[d] = m.xyz[3 * (size_t)g + d];
+    if (is_obj && tb.xyz.n) {
+        float d0[3] = {0.f, 0.f, 0.f}, d1[3] = {0.f, 0.f, 0.f};
+        lin_eval3_planar(m.xyz_deform, m.N_obj, j, tb.xyz, d0, d1, flow);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            xt[d] += d0[d];
+            xf[d] += d1[d];
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        xt[d] += s_bg[d];
+        xf[d] += s_bg[3 + d];
+    }
+
+    // ---- rotation ------------------------------------------------------------------------
+    float4 qraw;
+    if (is_obj) {
+        qraw = object_rotation_raw(m, tb, g, j, nullptr, nullptr);
+    } else {
+        qraw = reinterpret_cast<const float4*>(m.rotation)[g];
+    }
+    const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+    const float rot[4] = {qraw.x / qn, qraw.y / qn, qraw.z / qn, qraw.w / qn};
+
+    // ---- opacity, scale ------------------------------------------------------------------
+    float op = 1.0f / (1.0f + expf(-m.opacity[g]));
+    if (is_obj && tb.use_time_mask) {
+        const float delta = tb.t - m.gs_time[j];
+        const float2 sg = reinterpret_cast<const float2*>(m.gs_time_sigma)[j];
+        const float sigma = expf(delta < 0.0f ? sg.x : sg.y);
+        const float z = delta / sigma;
+        op *= expf(-0.5f * z * z);
+    }
+    float scale[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) scale[d] = expf(m.scaling[3 * (size_t)g + d]);
+
+    // ---- SH DC deformation ---------------------------------------------------------------
+    float dc[3];
+    const float4* sh4 = reinterpret_cast<const float4*>(m.sh4);
+    const float4 shq0 = __ldg(sh4 + g);
+    dc[0] = shq0.x;
+    dc[1] = shq0.y;
+    dc[2] = shq0.z;
+    if (tb.shs.n) {
+        // (3,Cs) block in float4 chunks; gather the term columns
+        const int Cs = tb.shs.n_cols;
+        const float* sd = m.shs_deform4;
+        for (int t = 0; t < tb.shs.n; ++t) {
+            const float w = tb.shs.w0[t];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int e = c * Cs + tb.shs.col[t];
+                dc[c] += __ldg(sd + ((size_t)(e >> 2) * N + g) * 4 + (e & 3)) * w;
+            }
+        }
+    }
+
+    // ---- optional materialised outputs (get_deformed_pkg shapes) ---------------------------
+    if (a.out.xyz) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a.out.xyz[3 * (size_t)g + d] = xt[d];
+    }
+    if (a.out.flow_xyz) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a.out.flow_xyz[3 * (size_t)g + d] = xf[d];
+    }
+    if (a.out.rotation) reinterpret_cast<float4*>(a.out.rotation)[g] = make_float4(rot[0], rot[1], rot[2], rot[3]);
+    if (a.out.opacity) a.out.opacity[g] = op;
+    if (a.out.scaling) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) a.out.scaling[3 * (size_t)g + d] = scale[d];
+    }
+    if (a.out.shs) {
+        float4* o = reinterpret_cast<float4*>(a.out.shs + (size_t)g * 48);
+        o[0] = make_float4(dc[0], dc[1], dc[2], shq0.w);
+#pragma unroll
+        for (int q = 1; q < 12; ++q) o[q] = __ldg(sh4 + (size_t)q * N + g);
+    }
+    if (!a.render) return;
+
+    // ---- rasterizer front end --------------------------------------------------------------
+    const float3 p = make_float3(xt[0], xt[1], xt[2]);
+    SplatGeom sg;
+    const bool visible = splat_geometry(p, scale, rot, nullptr, a.rp, cam.view, cam.proj, sg);
+    a.saved[(size_t)g * 3 + 0] = make_float4(xt[0], xt[1], xt[2], op);
+    a.saved[(size_t)g * 3 + 1] = make_float4(rot[0], rot[1], rot[2], rot[3]);
+    a.saved[(size_t)g * 3 + 2] = make_float4(dc[0], dc[1], dc[2], 0.f);
+    if (!visible) {
+        a.radii[g] = 0;
+        a.tiles_touched[g] = 0;
+        a.depth_keys[g] = 0xFFFFFFFFu;
+        return;
+    }
+    float sh[48];
+    const int deg = a.rp.sh_degree;
+    const int chunks = sh_chunks_for_degree(deg);
+    sh[0] = dc[0];
+    sh[1] = dc[1];
+    sh[2] = dc[2];
+    sh[3] = shq0.w;
+#pragma unroll
+    for (int q = 1; q < 12; ++q) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < chunks) v = __ldg(sh4 + (size_t)q * N + g);
+        sh[4 * q + 0] = v.x;
+        sh[4 * q + 1] = v.y;
+        sh[4 * q + 2] = v.z;
+        sh[4 * q + 3] = v.w;
+    }
+    float rgb[3];
+    uint32_t clamped;
+    sh_to_rgb(deg, p, cam.campos, sh, rgb, clamped);
+    a.clamped[g] = (uint8_t)clamped;
+    float2* c2 = reinterpret_cast<float2*>(a.cov3D + (size_t)g * 6);
+    c2[0] = make_float2(sg.cov3D[0], sg.cov3D[1]);
+    c2[1] = make_float2(sg.cov3D[2], sg.cov3D[3]);
+    c2[2] = make_float2(sg.cov3D[4], sg.cov3D[5]);
+    const float dfeat = a.rp.inv_depth ? (1.0f / (sg.depth + 0.0000001f)) : sg.depth;
+    const float sem0 = (a.render_objmask && is_obj) ? 1.f : 0.f;
+    float4* rec = a.record + (size_t)g * 4;
+    rec[0] = make_float4(sg.px, sg.py, sg.conic_x, sg.conic_y);
+    rec[1] = make_float4(sg.conic_z, op, rgb[0], rgb[1]);
+    rec[2] = make_float4(rgb[2], dfeat, flow ? xf[0] : 0.f, flow ? xf[1] : 0.f);
+    rec[3] = make_float4(flow ? xf[2] : 0.f, sem0, sg.depth, 0.f);
+    a.radii[g] = sg.radius;
+    a.tiles_touched[g] = sg.tiles;
+    a.depth_keys[g] = __float_as_uint(sg.depth);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+struct FusedBwdArgs {
+    adgs_model m;
+    adgs_model g;  // gradient buffers, same layouts
+    adgs_time_basis tb;
+    RasterParams rp;
+    const float* view;
+    const float* proj;
+    const float* campos;
+    const int32_t* radii;
+    const float* cov3D;
+    const uint8_t* clamped;
+    const float4* saved;
+    const float* grad_record;
+    float* dL_dmeans2D;
+    float4* dq_scratch;  // (N_obj) dL/d(normalised object quaternion)
+    float* bg_scratch;   // 6 floats: sum dxyz_t, sum dflow
+};
+
+__global__ void __launch_bounds__(256) fused_backward_kernel(const __grid_constant__ FusedBwdArgs a)
+{
+    __shared__ CamSmem cam;
+    __shared__ float s_wshs[ADGS_MAX_TERMS * 2];  // dense SH-deform weights per column
+    __shared__ float s_red[8][6];
+    const adgs_model& m = a.m;
+    const adgs_time_basis& tb = a.tb;
+    const int N = m.N_scene + m.N_obj;
+    const int Cs = tb.shs.n_cols;
+    for (int i = threadIdx.x; i < Cs && i < ADGS_MAX_TERMS * 2; i += blockDim.x) s_wshs[i] = 0.f;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int t = 0; t < tb.shs.n; ++t) s_wshs[tb.shs.col[t]] += tb.shs.w0[t];
+    load_camera(cam, a.view, a.proj, a.campos, nullptr);
+
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = g < N;
+    const bool is_obj = valid && g >= m.N_scene;
+    const int j = g - m.N_scene;
+    const bool flow = tb.has_flow != 0;
+    float dxt[3] = {0.f, 0.f, 0.f}, dfl[3] = {0.f, 0.f, 0.f};
+
+    if (valid) {
+        const float4* gr = reinterpret_cast<const float4*>(a.grad_record) + (size_t)g * 4;
+        const float4 g0 = gr[0], g1 = gr[1], g2 = gr[2], g3 = gr[3];
+        if (a.dL_dmeans2D) {
+            a.dL_dmeans2D[3 * (size_t)g + 0] = g0.x;
+            a.dL_dmeans2D[3 * (size_t)g + 1] = g0.y;
+            a.dL_dmeans2D[3 * (size_t)g + 2] = 0.f;
+        }
+        const bool visible = a.radii[g] > 0;
+        const float4 sv0 = a.saved[(size_t)g * 3 + 0];
+        const float4 sv1 = a.saved[(size_t)g * 3 + 1];
+        const float rot[4] = {sv1.x, sv1.y, sv1.z, sv1.w};
+        float scale[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) scale[d] = expf(m.scaling[3 * (size_t)g + d]);
+
+        float dscale[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
+        float dsh[48];
+#pragma unroll
+        for (int i = 0; i < 48; ++i) dsh[i] = 0.f;
+        if (flow) {
+            dfl[0] = g2.z;
+            dfl[1] = g2.w;
+            dfl[2] = g3.x;
+        }
+        if (visible) {
+            const float3 p = make_float3(sv0.x, sv0.y, sv0.z);
+            float cv[6], dcov[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) cv[i] = a.cov3D[(size_t)g * 6 + i];
+            float3 dm = cov2d_bwd(p, a.rp, cv, cam.view, g0.z, g0.w, g1.x, dcov);
+            const float3 dm2 = mean_proj_depth_bwd(p, cam.view, cam.proj, g0.x, g0.y, g2.y, a.rp.inv_depth);
+            const float4 sv2 = a.saved[(size_t)g * 3 + 2];
+            const float4* sh4 = reinterpret_cast<const float4*>(m.sh4);
+            float sh[48];
+            const int deg = a.rp.sh_degree;
+            const int chunks = sh_chunks_for_degree(deg);
+#pragma unroll
+            for (int q = 0; q < 12; ++q) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < chunks) v = __ldg(sh4 + (size_t)q * N + g);
+                sh[4 * q + 0] = v.x;
+                sh[4 * q + 1] = v.y;
+                sh[4 * q + 2] = v.z;
+                sh[4 * q + 3] = v.w;
+            }
+            sh[0] = sv2.x;
+            sh[1] = sv2.y;
+            sh[2] = sv2.z;
+            const float dcol[3] = {g1.z, g1.w, g2.x};
+            const float3 dm3 = sh_to_rgb_bwd(deg, p, cam.campos, sh, a.clamped[g], dcol, dsh);
+            dxt[0] = dm.x + dm2.x + dm3.x;
+            dxt[1] = dm.y + dm2.y + dm3.y;
+            dxt[2] = dm.z + dm2.z + dm3.z;
+            cov3d_bwd(scale, a.rp.scale_modifier, rot, dcov, dscale, dq);
+        }
+
+        // ---- leaf gradients ----------------------------------------------------------------
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            a.g.xyz[3 * (size_t)g + d] = dxt[d] + dfl[d];
+            a.g.scaling[3 * (size_t)g + d] = dscale[d] * scale[d];
+        }
+        float4* gsh4 = reinterpret_cast<float4*>(a.g.sh4);
+#pragma unroll
+        for (int q = 0; q < 12; ++q)
+            gsh4[(size_t)q * N + g] = make_float4(dsh[4 * q], dsh[4 * q + 1], dsh[4 * q + 2], dsh[4 * q + 3]);
+        if (a.g.shs_deform4 && Cs > 0) {
+            const int nq = (3 * Cs + 3) / 4;
+            float4* gsd = reinterpret_cast<float4*>(a.g.shs_deform4);
+            for (int q = 0; q < nq; ++q) {
+                float v[4];
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4) {
+                    const int e = 4 * q + e4;
+                    const int c = e / Cs;
+                    v[e4] = (c < 3) ? dsh[c] * s_wshs[e - c * Cs] : 0.f;
+                }
+                gsd[(size_t)q * N + g] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+        // opacity: op_act = sigmoid(o) [* mask]
+        {
+            const float dop = g1.y;
+            const float sig = 1.0f / (1.0f + expf(-m.opacity[g]));
+            float mask = 1.f;
+            if (is_obj && tb.use_time_mask) {
+                const float delta = tb.t - m.gs_time[j];
+                const float2 sgm = reinterpret_cast<const float2*>(m.gs_time_sigma)[j];
+                const bool neg = delta < 0.0f;
+                const float sigma = expf(neg ? sgm.x : sgm.y);
+                const float z = delta / sigma;
+                mask = expf(-0.5f * z * z);
+                const float dside = dop * sig * mask * z * z;
+                if (a.g.gs_time_sigma)
+                    reinterpret_cast<float2*>(a.g.gs_time_sigma)[j] = neg ? make_float2(dside, 0.f) : make_float2(0.f, dside);
+            } else if (is_obj && a.g.gs_time_sigma) {
+                reinterpret_cast<float2*>(a.g.gs_time_sigma)[j] = make_float2(0.f, 0.f);
+            }
+            a.g.opacity[g] = dop * mask * sig * (1.f - sig);
+        }
+        // rotation
+        if (!is_obj) {
+            const float4 qraw = reinterpret_cast<const float4*>(m.rotation)[g];
+            const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+            reinterpret_cast<float4*>(a.g.rotation)[g] =
+                normalize4_bwd(make_float4(rot[0], rot[1], rot[2], rot[3]), qn, make_float4(dq[0], dq[1], dq[2], dq[3]));
+        } else {
+            a.dq_scratch[j] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+        }
+        // position control points (dense elsewhere: zero-filled by the caller)
+        if (is_obj && tb.xyz.n && a.g.xyz_deform) {
+            for (int t = 0; t < tb.xyz.n; ++t) {
+                float* o = a.g.xyz_deform + ((size_t)tb.xyz.col[t] * 3) * m.N_obj + j;
+                const float w0 = tb.xyz.w0[t], w1 = tb.xyz.w1[t];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) o[(size_t)d * m.N_obj] = dxt[d] * w0 + dfl[d] * w1;
+            }
+        }
+    }
+
+    // ---- background parameter: grid reduction of sum dxyz_t / sum dflow -----------------------
+    if (tb.background.n) {
+        float r[6] = {dxt[0], dxt[1], dxt[2], dfl[0], dfl[1], dfl[2]};
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) r[i] += __shfl_xor_sync(0xffffffffu, r[i], off);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0)
+#pragma unroll
+            for (int i = 0; i < 6; ++i) s_red[warp][i] = r[i];
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
+            if (s != 0.f) atomicAdd(a.bg_scratch + threadIdx.x, s);
+        }
+    }
+}
+
+// Object rotation chain: normalised quaternion gradient -> static quaternion / linear terms /
+// control quaternions of the spline window.
+__global__ void __launch_bounds__(128) rotation_backward_kernel(const __grid_constant__ FusedBwdArgs a)
+{
+    const adgs_model& m = a.m;
+    const adgs_time_basis& tb = a.tb;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m.N_obj) return;
+    const int g = m.N_scene + j;
+    Quat qt[ADGS_MAX_QUAT_ORDER + 1];
+    float norms[ADGS_MAX_QUAT_ORDER + 1];
+    const float4 qraw = object_rotation_raw(m, tb, g, j, qt, norms);
+    const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+    const float4 qhat = make_float4(qraw.x / qn, qraw.y / qn, qraw.z / qn, qraw.w / qn);
+    const float4 graw = normalize4_bwd(qhat, qn, a.dq_scratch[j]);  // wxyz
+    reinterpret_cast<float4*>(a.g.rotation)[g] = (tb.quat.n_ctrl == 0) ? graw : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* grd = reinterpret_cast<float4*>(a.g.rot_deform);
+    if (!grd) return;
+    for (int t = 0; t < tb.rotation.n; ++t) {
+        const float w = tb.rotation.w0[t];
+        grd[(size_t)tb.rotation.col[t] * m.N_obj + j] = make_float4(graw.x * w, graw.y * w, graw.z * w, graw.w * w);
+    }
+    if (tb.quat.n_ctrl != 0) {
+        const int k = tb.quat.k;
+        Quat gqt[ADGS_MAX_QUAT_ORDER + 1];
+        quat_spline_bwd(qt, k, tb.quat.cum, Quat{graw.y, graw.z, graw.w, graw.x}, gqt);
+#pragma unroll
+        for (int i = 0; i <= ADGS_MAX_QUAT_ORDER; ++i) {
+            if (i <= k) {
+                // control = normalize(param + e_w): back through the normalisation, xyzw -> wxyz
+                const float4 nq = make_float4(qt[i].w, qt[i].x, qt[i].y, qt[i].z);
+                const float4 gg = make_float4(gqt[i].w, gqt[i].x, gqt[i].y, gqt[i].z);
+                grd[(size_t)(tb.quat.start + i) * m.N_obj + j] = normalize4_bwd(nq, norms[i], gg);
+            }
+        }
+    }
+}
+
+__global__ void background_finalize_kernel(const __grid_constant__ FusedBwdArgs a)
+{
+    const adgs_lin_basis& b = a.tb.background;
+    float* out = a.g.background_deform;
+    if (!out) return;
+    const int C = b.n_cols;
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) out[i] = 0.f;
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int d = threadIdx.x;
+        for (int t = 0; t < b.n; ++t) out[d * C + b.col[t]] += a.bg_scratch[d] * b.w0[t] + a.bg_scratch[3 + d] * b.w1[t];
+    }
+}
+
+int validate_model(const adgs_model* m, const adgs_time_basis* tb)
+{
+    if (!m || !tb) return ADGS_ERR_ARG;
+    if (m->N_scene < 0 || m->N_obj < 0) return ADGS_ERR_ARG;
+    const int N = m->N_scene + m->N_obj;
+    if (N == 0) return ADGS_OK;
+    if (!m->xyz || !m->scaling || !m->rotation || !m->opacity || !m->sh4) return ADGS_ERR_ARG;
+    const adgs_lin_basis* bs[4] = {&tb->xyz, &tb->background, &tb->shs, &tb->rotation};
+    for (int i = 0; i < 4; ++i) {
+        if (bs[i]->n < 0 || bs[i]->n > ADGS_MAX_TERMS) return ADGS_ERR_UNSUPPORTED;
+        for (int t = 0; t < bs[i]->n; ++t)
+            if (bs[i]->col[t] < 0 || bs[i]->col[t] >= bs[i]->n_cols) return ADGS_ERR_ARG;
+    }
+    if (tb->shs.n_cols > 2 * ADGS_MAX_TERMS) return ADGS_ERR_UNSUPPORTED;
+    if (tb->quat.k < 0 || tb->quat.k > ADGS_MAX_QUAT_ORDER) return ADGS_ERR_UNSUPPORTED;
+    if (m->N_obj > 0) {
+        if (tb->xyz.n && !m->xyz_deform) return ADGS_ERR_ARG;
+        if ((tb->rotation.n || tb->quat.n_ctrl) && !m->rot_deform) return ADGS_ERR_ARG;
+        if (tb->use_time_mask && (!m->gs_time || !m->gs_time_sigma)) return ADGS_ERR_ARG;
+    }
+    if (tb->shs.n && !m->shs_deform4) return ADGS_ERR_ARG;
+    if (tb->background.n && !m->background_deform) return ADGS_ERR_ARG;
+    return ADGS_OK;
+}
+
+}  // namespace
+}  // namespace adgs
+
+using namespace adgs;
+
+extern "C" {
+
+int adgs_trajectory_forward(const adgs_model* model, const adgs_time_basis* basis, const adgs_deformed* out,
+                            adgs_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st = validate_model(model, basis);
+    if (st) return st;
+    if (!out) return ADGS_ERR_ARG;
+    const int N = model->N_scene + model->N_obj;
+    if (N == 0) return ADGS_OK;
+    FusedFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = *model;
+    a.tb = *basis;
+    a.out = *out;
+    a.render = 0;
+    fused_forward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+    return check_stage("trajectory forward", false, stream);
+}
+
+size_t adgs_render_saved_bytes(int32_t N)
+{
+    return (size_t)(N > 0 ? N : 0) * kSavedFloats * sizeof(float) + 256;
+}
+
+int adgs_render_forward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
+                        int32_t render_objmask, const adgs_images* out, const adgs_deformed* deformed,
+                        char* geometry, char* binning, int64_t capacity, adgs_alloc_fn binning_alloc,
+                        void* alloc_user, char* image, char* saved, adgs_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st = validate_model(model, basis);
+    if (st) return st;
+    if (!cam || !out || !geometry || !image || !saved || capacity < 0) return ADGS_ERR_ARG;
+    if (!binning && !binning_alloc) return ADGS_ERR_ARG;
+    if (!out->depth || !out->opacity || !cam->viewmatrix || !cam->projmatrix || !cam->campos || !cam->bg)
+        return ADGS_ERR_ARG;
+    if (cam->sh_degree < 0 || cam->sh_degree > 3) return ADGS_ERR_UNSUPPORTED;
+    const int N = model->N_scene + model->N_obj;
+    if (N == 0) return ADGS_ERR_ARG;
+    GeometryState gs = GeometryState::from_chunk(geometry, (size_t)N);
+    ImageState is = ImageState::from_chunk(image, cam->image_width, cam->image_height);
+    cudaMemsetAsync(gs.counters, 0, 32 * sizeof(uint32_t), stream);
+    int32_t* radii = out->radii ? out->radii : gs.radii;
+
+    FusedFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = *model;
+    a.tb = *basis;
+    if (deformed) a.out = *deformed;
+    a.render = 1;
+    a.render_objmask = render_objmask;
+    a.rp = make_raster_params(cam);
+    a.view = cam->viewmatrix;
+    a.proj = cam->projmatrix;
+    a.campos = cam->campos;
+    a.radii = radii;
+    a.depth_keys = gs.depth_keys;
+    a.tiles_touched = gs.tiles_touched;
+    a.record = reinterpret_cast<float4*>(gs.record);
+    a.cov3D = gs.cov3D;
+    a.clamped = gs.clamped;
+    char* sc = saved;
+    carve(sc, a.saved, (size_t)N * 3);
+    fused_forward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+    st = check_stage("fused forward", cam->debug != 0, stream);
+    if (st) return st;
+    int R = 0;
+    st = bin_and_blend(cam, N, render_objmask ? 1 : 0, basis->has_flow != 0, nullptr, out, radii, gs, binning,
+                       binning_alloc, alloc_user, capacity, is, binning == nullptr, &R, stream);
+    return st ? st : R;
+}
+
+size_t adgs_render_scratch_bytes(int32_t N, int32_t N_obj)
+{
+    return (size_t)(N > 0 ? N : 0) * ADGS_GRAD_FLOATS * sizeof(float) + (size_t)(N_obj > 0 ? N_obj : 1) * 16 + 1024;
+}
+
+int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
+                         int32_t render_objmask, const int32_t* radii, const char* geometry, const char* binning,
+                         int64_t capacity, const char* image, const char* saved, const float* img_opacity,
+                         const adgs_image_grads* dpix, const adgs_model* grads, float* dL_dmeans2D, char* scratch,
+                         adgs_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st = validate_model(model, basis);
+    if (st) return st;
+    if (!cam || !geometry || !binning || !image || !saved || !img_opacity || !dpix || !grads || !scratch ||
+        capacity < 0)
+        return ADGS_ERR_ARG;
+    if (!grads->xyz || !grads->scaling || !grads->rotation || !grads->opacity || !grads->sh4) return ADGS_ERR_ARG;
+    const int N = model->N_scene + model->N_obj;
+    if (N == 0) return ADGS_ERR_ARG;
+    const bool debug = cam->debug != 0;
+    const RasterParams rp = make_raster_params(cam);
+    char* gc = const_cast<char*>(geometry);
+    char* bc = const_cast<char*>(binning);
+    char* ic = const_cast<char*>(image);
+    char* svc = const_cast<char*>(saved);
+    GeometryState gs = GeometryState::from_chunk(gc, (size_t)N);
+    BinningState bs = BinningState::from_chunk(bc, (size_t)capacity);
+    ImageState is = ImageState::from_chunk(ic, rp.W, rp.H);
+    if (!radii) radii = gs.radii;
+
+    char* sc = scratch;
+    float* grad_record = nullptr;
+    float4* dq_scratch = nullptr;
+    float* bg_scratch = nullptr;
+    carve(sc, grad_record, (size_t)N * ADGS_GRAD_FLOATS);
+    carve(sc, dq_scratch, (size_t)(model->N_obj > 0 ? model->N_obj : 1));
+    carve(sc, bg_scratch, 32);
+    cudaMemsetAsync(grad_record, 0, (size_t)N * ADGS_GRAD_FLOATS * sizeof(float), stream);
+    cudaMemsetAsync(bg_scratch, 0, 32 * sizeof(float), stream);
+
+    const bool has_flow = basis->has_flow != 0;
+    BlendBwdArgs b;
+    b.ranges = is.ranges;
+    b.point_list = sorted_point_list(bs, rp.grid_x * rp.grid_y);
+    b.record = reinterpret_cast<const float4*>(gs.record);
+    b.semantic = nullptr;
+    b.bg = cam->bg;
+    b.W = rp.W;
+    b.H = rp.H;
+    b.D_S = render_objmask ? 1 : 0;
+    b.n_contrib = is.n_contrib;
+    b.img_opacity = img_opacity;
+    b.dL_dcolor = dpix->dL_dcolor;
+    b.dL_ddepth = dpix->dL_ddepth;
+    b.dL_dflow = has_flow ? dpix->dL_dflow : nullptr;
+    b.dL_dsemantic = nullptr;  // the object mask is a constant: no gradient flows into it
+    b.dL_dopacity = dpix->dL_dopacity;
+    b.grad_record = grad_record;
+    b.dL_dsemantic_g = nullptr;
+    if (capacity > 0) {
+        launch_blend_backward(b, has_flow, stream);
+        if ((st = check_stage("blend backward", debug, stream))) return st;
+    }
+
+    // dense-gradient semantics: everything outside the active columns is zero
+    const int No = model->N_obj;
+    if (No > 0 && grads->xyz_deform && basis->xyz.n_cols > 0)
+        cudaMemsetAsync(grads->xyz_deform, 0, (size_t)basis->xyz.n_cols * 3 * No * sizeof(float), stream);
+    const int Cr = basis->rotation.n_cols;
+    if (No > 0 && grads->rot_deform && Cr > 0)
+        cudaMemsetAsync(grads->rot_deform, 0, (size_t)Cr * No * 4 * sizeof(float), stream);
+
+    FusedBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = *model;
+    a.g = *grads;
+    a.tb = *basis;
+    a.rp = rp;
+    a.view = cam->viewmatrix;
+    a.proj = cam->projmatrix;
+    a.campos = cam->campos;
+    a.radii = radii;
+    a.cov3D = gs.cov3D;
+    a.clamped = gs.clamped;
+    char* svp = svc;
+    float4* saved4 = nullptr;
+    carve(svp, saved4, (size_t)N * 3);
+    a.saved = saved4;
+    a.grad_record = grad_record;
+    a.dL_dmeans2D = dL_dmeans2D;
+    a.dq_scratch = dq_scratch;
+    a.bg_scratch = bg_scratch;
+    fused_backward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+    if ((st = check_stage("fused backward", debug, stream))) return st;
+    if (No > 0) {
+        rotation_backward_kernel<<<(No + 127) / 128, 128, 0, stream>>>(a);
+        if ((st = check_stage("rotation backward", debug, stream))) return st;
+    }
+    if (grads->background_deform && basis->background.n_cols > 0) {
+        background_finalize_kernel<<<1, 128, 0, stream>>>(a);
+        if ((st = check_stage("background finalize", debug, stream))) return st;
+    }
+    return ADGS_OK;
+}
+
+}  // extern "C"

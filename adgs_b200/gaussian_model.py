@@ -1,0 +1,330 @@
+"""Host-side mirror of the hot-path part of `scene/gaussian_model.py:GaussianModel`.
+
+Same names and meaning for everything `gaussian_renderer.render()` touches
+(`get_xyz`, `get_scaling`, `get_obj_mask`, `get_deformed_xyz`, `get_deformed_pkg`,
+`active_sh_degree`, `order_args`, ... scene/gaussian_model.py:88-231), but the parameters live in
+the B200 layout of include/adgs_b200.h:adgs_model -- Gaussians ordered [scene ; object], wide
+per-Gaussian blocks planar so that warps read whole 128-byte lines:
+
+    xyz (N,3)  scaling (N,3)  rotation (N,4)  opacity (N,1)             raw, pre-activation
+    sh4 (12,N,4)                 the (16,3) SH block, flattened, in float4 chunks
+    shs_deform4 (ceil(3*Cs/4),N,4)
+    xyz_deform (Cx,3,N_obj)      rot_deform (Cr,N_obj,4)      background_deform (3,Cb)
+    gs_time (N_obj,)             gs_time_sigma (N_obj,2)
+
+`from_reference()` / `to_reference()` convert from / to the reference's tensors
+(`_scene_xyz`, `_obj_xyz`, `xyz_deform_param (N_obj,3,Cx)`, ... gaussian_model.py:46-84,285-328),
+so checkpoints and parity tests speak the reference layout.
+
+Optimizer / densification / PLY code is out of scope.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib as L
+
+DEFAULT_ORDER_ARGS = {  # arguments/__init__.py:71-77
+    'xyz': [None, None, 0, None, 0, 0],
+    'rotation': [0, 0, 0, 0, None, None],
+    'shs': [0, 0, 0, None, 0, 0],
+    'background': [0, 0, 0, 0, 0, 0],
+}
+
+
+def get_param_num(args):
+    """utils/func_utils.py:79-80"""
+    return args[0] + args[2] + 2 * args[3] + args[4]
+
+
+def set_default_param_order(order_args: dict, frame_num: int, downsample_ratio: int = 3):
+    """utils/func_utils.py:82-119: fill the `None`s of the per-attribute 6-tuples
+    [bspline_ctrl, bspline_order, poly, fft, quat_ctrl, quat_order]."""
+    res = dict()
+    for k, v in order_args.items():
+        a = v if v is not None else [None] * 6
+        assert a[0] is None or a[0] >= 0, f'The B-Spline ctrl pts num cannot be negative in {k}, but find {a[0]}.'
+        n_b = a[0] if a[0] is not None else int(frame_num // downsample_ratio)
+        k_b = 0
+        if n_b > 0:
+            assert a[1] is None or a[1] >= 0, f'The B-Spline order cannot be negative in {k}, but find {a[1]}.'
+            if a[1] is not None and a[1] + 1 > n_b:
+                print('[WARNING] The B-Spline order should be lower than the ctrl pts num. Set order to', n_b - 1)
+            k_b = min(a[1] if a[1] is not None else 5, n_b - 1)
+        assert a[2] is None or a[2] >= 0, f'The poly order cannot be negative in {k}, but find {a[2]}.'
+        n_poly = a[2] if a[2] is not None else int(frame_num // downsample_ratio)
+        assert a[3] is None or a[3] >= 0, f'The fft order cannot be negative in {k}, but find {a[3]}.'
+        n_fft = a[3] if a[3] is not None else 6
+        assert a[4] is None or a[4] >= 0, \
+            f'The quaternion spline ctrl pts num cannot be negative in {k}, but find {a[4]}.'
+        n_q = a[4] if a[4] is not None else int(frame_num // downsample_ratio)
+        k_q = 0
+        if n_q > 0:
+            assert a[5] is None or a[5] >= 0, f'The quaternion spline order cannot be negative in {k}, but find {a[5]}.'
+            if a[5] is not None and a[5] + 1 > n_q:
+                print('[WARNING] The quaternion spline order should be lower than the ctrl pts num. Set order to',
+                      n_q - 1)
+            k_q = min(a[5] if a[5] is not None else 1, n_q - 1)
+        res[k] = [n_b, k_b, n_poly, n_fft, n_q, k_q]
+    return res
+
+
+_M = {}
+
+
+def deboor_cox_matrix(order: int) -> np.ndarray:
+    """Uniform B-spline basis matrix M_k, B(u) = [1,u,...,u^k] M_k, via the de Boor-Cox recursion
+    (same float32 arithmetic as utils/func_utils.py:33-50 so M_1..M_5 are identical)."""
+    if order in _M:
+        return _M[order]
+    if order == 0:
+        m = np.array([[1.0]], dtype=np.float32)
+    else:
+        prev = deboor_cox_matrix(order - 1)
+        z = np.zeros((1, prev.shape[1]), dtype=np.float32)
+        up, lo = np.concatenate([prev, z], 0), np.concatenate([z, prev], 0)
+        a = np.zeros((order, order + 1), dtype=np.float32)
+        b = np.zeros((order, order + 1), dtype=np.float32)
+        i = np.arange(order)
+        a[i, i] = i + 1
+        a[i, i + 1] = order - i - 1
+        b[i, i] = -1
+        b[i, i + 1] = 1
+        m = (up @ a + lo @ b) / order
+    _M[order] = m
+    return m
+
+
+def _bspline_window(v: float, n: int, k: int):
+    """(first control index, basis values) of func_utils.py:127-132."""
+    interval = n - k
+    start = min(int(v * interval), interval - 1)
+    u = v * interval - start
+    powers = np.array([u ** i for i in range(k + 1)], dtype=np.float64)
+    return start, powers @ deboor_cox_matrix(k).astype(np.float64)
+
+
+def linear_terms(v: float, args):
+    """{column: weight} such that get_func_result's linear part == sum_c param[..., c] * weight[c]
+    (B-spline window + polynomial + Fourier, func_utils.py:127-153)."""
+    n_b, k_b, n_poly, n_fft, n_q, k_q = args
+    terms, off = {}, 0
+    if n_b != 0:
+        s, basis = _bspline_window(v, n_b, k_b)
+        for j in range(k_b + 1):
+            terms[off + s + j] = float(basis[j])
+        off += n_b
+    if n_poly != 0:
+        for i in range(1, n_poly + 1):
+            terms[off + i - 1] = float(v ** i)
+        off += n_poly
+    if n_fft != 0:
+        for i in range(1, n_fft + 1):
+            terms[off + i - 1] = math.sin(v * i * math.pi)
+            terms[off + n_fft + i - 1] = math.cos(v * i * math.pi)
+        off += 2 * n_fft
+    return terms, off
+
+
+def _fill_lin(dst: L.LinBasis, args, t, t2=None):
+    terms0, _ = linear_terms(t, args)
+    terms1 = linear_terms(t2, args)[0] if t2 is not None else {}
+    cols = sorted(set(terms0) | set(terms1))
+    if len(cols) > L.MAX_TERMS:
+        raise ValueError(f"{len(cols)} active trajectory columns exceed ADGS_MAX_TERMS={L.MAX_TERMS}")
+    dst.n = len(cols)
+    dst.n_cols = get_param_num(args)
+    for i, c in enumerate(cols):
+        dst.col[i] = c
+        dst.w0[i] = terms0.get(c, 0.0)
+        dst.w1[i] = terms1.get(c, 0.0)
+
+
+def make_time_basis(order_args, t: float, flow_t=None, use_time_mask=True) -> L.TimeBasis:
+    """Everything time-dependent the kernels need for one render, computed on the host in float64
+    (the reference also derives segment index and u on the host, func_utils.py:128-132)."""
+    tb = L.TimeBasis()
+    _fill_lin(tb.xyz, order_args['xyz'], t, flow_t)
+    _fill_lin(tb.background, order_args['background'], t, flow_t)
+    _fill_lin(tb.shs, order_args['shs'], t)
+    ra = order_args['rotation']
+    _fill_lin(tb.rotation, ra, t)
+    tb.quat.n_ctrl, tb.quat.k = ra[4], ra[5]
+    if ra[4] != 0:
+        if ra[5] > L.MAX_QUAT_ORDER:
+            raise ValueError("quaternion spline order > 7 is not supported")
+        s, basis = _bspline_window(t, ra[4], ra[5])
+        tb.quat.start = ra[0] + ra[2] + 2 * ra[3] + s
+        for i in range(1, ra[5] + 1):
+            tb.quat.cum[i] = float(basis[i:].sum())
+    tb.t = float(t)
+    tb.use_time_mask = int(bool(use_time_mask))
+    tb.has_flow = int(flow_t is not None)
+    return tb
+
+
+PARAM_NAMES = ("xyz", "scaling", "rotation", "opacity", "sh4", "shs_deform4", "xyz_deform", "rot_deform",
+               "background_deform", "gs_time_sigma")
+
+
+class GaussianModel(nn.Module):
+    """Hot-path subset of scene/gaussian_model.py:GaussianModel over planar B200 storage."""
+
+    def __init__(self, sh_degree: int, order_args: dict):
+        super().__init__()
+        self.active_sh_degree = 0
+        self.max_sh_degree = sh_degree
+        self.order_args = order_args
+        self.use_time_mask = True
+        self.n_scene = 0
+        self.n_obj = 0
+        self._binning_capacity = 0   # running bound on num_rendered for the sync-free path
+        self._pending = None         # (pinned counters, event) of the last sync-free forward
+
+    # ---- construction ------------------------------------------------------------------------
+    @classmethod
+    def from_reference(cls, ref: dict, order_args: dict, sh_degree=3, use_time_mask=True, device="cuda"):
+        """ref: the reference's tensors by attribute name without the leading underscore
+        (scene_xyz, obj_xyz, scene_shs_dc, ..., xyz_deform_param, ..., gs_time, gs_time_sigma)."""
+        m = cls(sh_degree, order_args)
+        m.use_time_mask = use_time_mask
+        g = lambda k: ref[k].detach().to(device=device, dtype=torch.float32)
+        cat = lambda a, b: torch.cat([g(a), g(b)], dim=0)
+        m.n_scene, m.n_obj = ref["scene_xyz"].shape[0], ref["obj_xyz"].shape[0]
+        n, no = m.n_scene + m.n_obj, m.n_obj
+        shs = torch.cat([cat("scene_shs_dc", "obj_shs_dc"), cat("scene_shs_rest", "obj_shs_rest")], dim=1)  # (N,16,3)
+        shsd = cat("shs_deform_param_scene", "shs_deform_param_obj").reshape(n, -1)                        # (N,3*Cs)
+        pad = (-shsd.shape[1]) % 4
+        if pad:
+            shsd = torch.cat([shsd, shsd.new_zeros(n, pad)], dim=1)
+        params = dict(
+            xyz=cat("scene_xyz", "obj_xyz"), scaling=cat("scene_scaling", "obj_scaling"),
+            rotation=cat("scene_rotation", "obj_rotation"), opacity=cat("scene_opacity", "obj_opacity"),
+            sh4=shs.reshape(n, 12, 4).permute(1, 0, 2), shs_deform4=shsd.reshape(n, -1, 4).permute(1, 0, 2),
+            xyz_deform=g("xyz_deform_param").permute(2, 1, 0), rot_deform=g("rotation_deform_param").permute(2, 0, 1),
+            background_deform=g("background_deform_param").reshape(3, -1), gs_time_sigma=g("gs_time_sigma"))
+        for k, v in params.items():
+            setattr(m, k, nn.Parameter(v.contiguous().clone()))
+        m.register_buffer("gs_time", g("gs_time").reshape(no).contiguous().clone())
+        m.active_sh_degree = sh_degree
+        return m
+
+    def to_reference(self, grads=False) -> dict:
+        """Inverse of from_reference (parameters, or their .grad when grads=True)."""
+        pick = (lambda p: p.grad) if grads else (lambda p: p.detach())
+        ns, n = self.n_scene, self.n_scene + self.n_obj
+        xyz, sc, rot, op = pick(self.xyz), pick(self.scaling), pick(self.rotation), pick(self.opacity)
+        shs = pick(self.sh4).permute(1, 0, 2).reshape(n, 16, 3)
+        cs = get_param_num(self.order_args['shs'])
+        shsd = pick(self.shs_deform4).permute(1, 0, 2).reshape(n, -1)[:, :3 * cs].reshape(n, 3, cs)
+        out = dict(
+            scene_xyz=xyz[:ns], obj_xyz=xyz[ns:], scene_scaling=sc[:ns], obj_scaling=sc[ns:],
+            scene_rotation=rot[:ns], obj_rotation=rot[ns:], scene_opacity=op[:ns], obj_opacity=op[ns:],
+            scene_shs_dc=shs[:ns, 0:1], obj_shs_dc=shs[ns:, 0:1], scene_shs_rest=shs[:ns, 1:], obj_shs_rest=shs[ns:, 1:],
+            shs_deform_param_scene=shsd[:ns], shs_deform_param_obj=shsd[ns:],
+            xyz_deform_param=pick(self.xyz_deform).permute(2, 1, 0),
+            rotation_deform_param=pick(self.rot_deform).permute(1, 2, 0),
+            background_deform_param=pick(self.background_deform).reshape(1, 3, -1),
+            gs_time_sigma=pick(self.gs_time_sigma))
+        if not grads:
+            out["gs_time"] = self.gs_time.reshape(-1, 1)
+        return out
+
+    def hot_parameters(self):
+        return [getattr(self, k) for k in PARAM_NAMES]
+
+    # ---- reference-named accessors (scene/gaussian_model.py:88-171) ---------------------------
+    @property
+    def get_pts_num(self):
+        return self.n_scene + self.n_obj
+
+    @property
+    def get_scene_pts_num(self):
+        return self.n_scene
+
+    @property
+    def get_obj_pts_num(self):
+        return self.n_obj
+
+    @property
+    def get_xyz(self):
+        return self.xyz
+
+    @property
+    def get_scaling(self):
+        return torch.exp(self.scaling)
+
+    @property
+    def get_rotation(self):
+        return torch.nn.functional.normalize(self.rotation)
+
+    @property
+    def get_opacity(self):
+        return torch.sigmoid(self.opacity)
+
+    @property
+    def get_shs(self):
+        n = self.get_pts_num
+        return self.sh4.permute(1, 0, 2).reshape(n, 16, 3)
+
+    @property
+    def get_obj_mask(self):
+        mask = torch.zeros((self.get_pts_num,), dtype=torch.bool, device=self.xyz.device)
+        mask[self.n_scene:] = True
+        return mask
+
+    def oneupSHdegree(self):
+        if self.active_sh_degree < self.max_sh_degree:
+            self.active_sh_degree += 1
+
+    # ---- C-ABI views ----------------------------------------------------------------------------
+    def c_model_from(self, t: dict, with_time=True) -> L.Model:
+        """adgs_model over the given tensors (parameters, or gradient buffers with with_time=False)."""
+        return L.Model(N_scene=self.n_scene, N_obj=self.n_obj, xyz=L.ptr(t["xyz"]), scaling=L.ptr(t["scaling"]),
+                       rotation=L.ptr(t["rotation"]), opacity=L.ptr(t["opacity"]), sh4=L.ptr(t["sh4"]),
+                       shs_deform4=L.ptr(t["shs_deform4"]), xyz_deform=L.ptr(t["xyz_deform"]),
+                       rot_deform=L.ptr(t["rot_deform"]), background_deform=L.ptr(t["background_deform"]),
+                       gs_time=L.ptr(self.gs_time) if with_time else None, gs_time_sigma=L.ptr(t["gs_time_sigma"]))
+
+    def c_model(self) -> L.Model:
+        return self.c_model_from({k: getattr(self, k) for k in PARAM_NAMES})
+
+    def _note_num_rendered(self, R: int):
+        """Sync-free binning: keep the arena 30 % above the largest num_rendered seen so far."""
+        self._binning_capacity = max(self._binning_capacity, int(1.3 * R) + 65536)
+
+    def time_basis(self, t, flow_t=None) -> L.TimeBasis:
+        return make_time_basis(self.order_args, t, flow_t, self.use_time_mask)
+
+    # ---- trajectory alone (drop-in for get_deformed_* ; values only, see gaussian_renderer.render for grads)
+    @torch.no_grad()
+    def _deform(self, t, flow_t=None, want=("xyz", "rotation", "shs", "opacity")):
+        lib = L.load()
+        n, dev = self.get_pts_num, self.xyz.device
+        shapes = dict(xyz=(n, 3), rotation=(n, 4), shs=(n, 16, 3), opacity=(n, 1), scaling=(n, 3), flow_xyz=(n, 3))
+        out = {k: torch.empty(shapes[k], dtype=torch.float32, device=dev) for k in want}
+        d = L.Deformed(**{k: L.ptr(out.get(k)) for k in shapes})
+        tb = self.time_basis(t, flow_t)
+        with torch.cuda.device(dev):
+            st = lib.adgs_trajectory_forward(C.byref(self.c_model()), C.byref(tb), C.byref(d),
+                                             torch.cuda.current_stream(dev).cuda_stream)
+        L.check(st, "trajectory_forward")
+        return out
+
+    def get_deformed_xyz(self, t):
+        return self._deform(t, want=("xyz",))["xyz"]
+
+    def get_deformed_rotation(self, t):
+        return self._deform(t, want=("rotation",))["rotation"]
+
+    def get_deformed_shs(self, t):
+        return self._deform(t, want=("shs",))["shs"]
+
+    def get_time_masked_opacity(self, t):
+        return self._deform(t, want=("opacity",))["opacity"]
+
+    def get_deformed_pkg(self, t):
+        return self._deform(t)

@@ -303,15 +303,21 @@ typedef struct adgs_deformed {
 ADGS_API int adgs_trajectory_forward(const adgs_model* model, const adgs_time_basis* basis,
                             const adgs_deformed* out, adgs_stream_t stream);
 
-/* Fused render forward: trajectory + preprocess + binning + blend, no host synchronisation.
+/* Fused render forward: trajectory + preprocess + binning + blend.
  * semantic = object mask (render_objmask=True, gaussian_renderer/__init__.py:71-73) when
- * `render_objmask` != 0. Arenas as in adgs_rasterize_forward_async. `saved` (N*8 floats) keeps
- * what the backward needs from the trajectory (xyz(t), activated opacity, ...). */
+ * `render_objmask` != 0. Two binning modes:
+ *   - `binning` != null: caller-provided arena of adgs_binning_bytes(capacity); NO host
+ *     synchronisation; returns 0. Overflow is reported through adgs_read_counters().
+ *   - `binning` == null: `binning_alloc` is called with the exact size after one blocking 4-byte
+ *     read of num_rendered (the reference's behaviour, rasterizer_impl.cu:288); returns num_rendered.
+ * `saved` (adgs_render_saved_bytes(N)) keeps what the backward needs from the trajectory
+ * (xyz(t), activated opacity, normalised rotation, deformed SH DC). */
 ADGS_API size_t adgs_render_saved_bytes(int32_t N);
+ADGS_API size_t adgs_render_scratch_bytes(int32_t N, int32_t N_obj);
 ADGS_API int adgs_render_forward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
                         int32_t render_objmask, const adgs_images* out, const adgs_deformed* deformed,
-                        char* geometry, char* binning, int64_t capacity, char* image, char* saved,
-                        adgs_stream_t stream);
+                        char* geometry, char* binning, int64_t capacity, adgs_alloc_fn binning_alloc,
+                        void* alloc_user, char* image, char* saved, adgs_stream_t stream);
 
 /* Fused render backward: blend backward + preprocess backward + trajectory backward, writing
  * DENSE parameter gradients in the model layouts (zeros outside the B-spline windows, which is
@@ -319,7 +325,7 @@ ADGS_API int adgs_render_forward(const adgs_camera* cam, const adgs_model* model
  * gradient dL_dmeans2D (N,3) used by densification (gaussian_model.py:863-867). */
 ADGS_API int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
                          int32_t render_objmask, const int32_t* radii, const char* geometry,
-                         const char* binning, const char* image, const char* saved,
+                         const char* binning, int64_t capacity, const char* image, const char* saved,
                          const float* img_opacity, const adgs_image_grads* dpix,
                          const adgs_model* grads, float* dL_dmeans2D, char* scratch,
                          adgs_stream_t stream);

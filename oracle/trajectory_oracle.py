@@ -271,7 +271,7 @@ def random_reference_model(n_scene, n_obj, order_args, seed=0, device="cpu", dty
         shs_deform_param_obj=U(n_obj, 3, Cs, scale=deform_scale),
         background_deform_param=U(1, 3, Cb, scale=deform_scale),
         gs_time=(torch.rand(n_obj, 1, generator=g, dtype=torch.float64)).to(dtype).to(device),
-        gs_time_sigma=torch.full((n_obj, 2), math.log(1.0 / 96.0)).to(dtype).to(device) + U(n_obj, 2, scale=2.0),
+        gs_time_sigma=U(n_obj, 2, scale=0.75) - 0.75,   # sigma in (0.22, 1): the time mask stays well above 0
     )
     t = {k: v.clone().contiguous() for k, v in t.items()}
     if requires_grad:

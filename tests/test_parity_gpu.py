@@ -182,10 +182,11 @@ def test_autograd_module_matches_reference_semantics():
         (img_flow * cot["flow"]).sum()).add((img_sem * cot["semantic"]).sum()).backward()
     raw = Hh.OURS.rasterize_gaussians(*Hh.fwd_args(c))
     g = Hh.OURS.rasterize_gaussians_backward(*Hh.bwd_args(c, raw, cot), opacities=c["opacity"])
-    assert torch.allclose(means2D.grad, g[0]) and torch.allclose(leaves["means3D"].grad, g[3])
-    assert torch.allclose(leaves["sh"].grad, g[5]) and torch.allclose(leaves["opacity"].grad, g[2])
-    assert torch.allclose(leaves["scales"].grad, g[6]) and torch.allclose(leaves["rotations"].grad, g[7])
-    assert torch.allclose(leaves["flow_points"].grad, g[8])
+    # two runs differ only by the order of the float atomics
+    for got, want in ((means2D.grad, g[0]), (leaves["means3D"].grad, g[3]), (leaves["sh"].grad, g[5]),
+                      (leaves["opacity"].grad, g[2]), (leaves["scales"].grad, g[6]), (leaves["rotations"].grad, g[7]),
+                      (leaves["flow_points"].grad, g[8])):
+        assert got.shape == want.shape and Hh.rel_err(got, want) <= 1e-5
     with pytest.raises(Exception):
         GaussianRasterizer(settings)(means3D=c["means3D"], means2D=means2D, opacities=c["opacity"], shs=c["sh"],
                                      colors_precomp=c["sh"][:, 0], scales=c["scales"], rotations=c["rotations"])
