@@ -215,6 +215,11 @@ SIGNATURES = {
     "adgs_render_backward": (C.c_int, [_P(Camera), _P(Model), _P(TimeBasis), C.c_int32, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, _P(ImageGrads),
                                        _P(Model), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adgs_launch_count": (C.c_ulonglong, []),
+    "adgs_profile_begin": (C.c_int, []),
+    "adgs_profile_num_stages": (C.c_int, []),
+    "adgs_profile_stage_name": (C.c_char_p, [C.c_int]),
+    "adgs_profile_end": (C.c_int, [C.c_void_p, C.c_void_p]),
     "adgs_knn_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "adgs_dist_cuda2": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

@@ -56,13 +56,19 @@ int bin_and_blend(const adgs_camera* cam, int P, int D_S, bool has_flow, const f
     int st;
 
     // (1) Gaussians by (depth bits, id): 4 onesweep passes over 8 B/Gaussian.
-    sort_pairs_async(gs.depth_keys, gs.depth_keys_alt, gs.order_a, gs.order_b, (size_t)P, nullptr, 0, 32, gs.sort,
-                     /*iota*/ true, /*clear*/ true, stream);
+    {
+        StageScope sc(kStageDepthSort, stream);
+        sort_pairs_async(gs.depth_keys, gs.depth_keys_alt, gs.order_a, gs.order_b, (size_t)P, nullptr, 0, 32, gs.sort,
+                         /*iota*/ true, /*clear*/ true, stream);
+    }
     if ((st = check_stage("depth sort", debug, stream))) return st;
 
     // (2) offsets of every Gaussian's tile instances, in depth order; total -> counters[0]
-    inclusive_scan_gather_async(gs.tiles_touched, gs.depth_order, gs.point_offsets, (size_t)P, gs.scan_status,
-                                gs.counters, stream);
+    {
+        StageScope sc(kStageScan, stream);
+        inclusive_scan_gather_async(gs.tiles_touched, gs.depth_order, gs.point_offsets, (size_t)P, gs.scan_status,
+                                    gs.counters, stream);
+    }
     if ((st = check_stage("scan", debug, stream))) return st;
 
     if (sync_for_count) {
@@ -81,14 +87,23 @@ int bin_and_blend(const adgs_camera* cam, int P, int D_S, bool has_flow, const f
     const uint32_t* point_list = bs.vals_a;
     if (capacity > 0) {
         // (3) instances in depth order, (4) stable sort by tile id only
-        launch_emit(P, gs.depth_order, gs.point_offsets, gs.tiles_touched, reinterpret_cast<const float4*>(gs.record),
-                    radii, rp.grid_x, rp.grid_y, bs.keys_a, bs.vals_a, (uint32_t)capacity, gs.counters, stream);
+        {
+            StageScope sc(kStageEmit, stream);
+            launch_emit(P, gs.depth_order, gs.point_offsets, gs.tiles_touched,
+                        reinterpret_cast<const float4*>(gs.record), radii, rp.grid_x, rp.grid_y, bs.keys_a, bs.vals_a,
+                        (uint32_t)capacity, gs.counters, stream);
+        }
         if ((st = check_stage("emit", debug, stream))) return st;
-        const int passes = sort_pairs_async(bs.keys_a, bs.keys_b, bs.vals_a, bs.vals_b, (size_t)capacity, gs.counters,
-                                            0, tile_id_bits(num_tiles), bs.sort, false, true, stream);
+        int passes;
+        {
+            StageScope sc(kStageTileSort, stream);
+            passes = sort_pairs_async(bs.keys_a, bs.keys_b, bs.vals_a, bs.vals_b, (size_t)capacity, gs.counters, 0,
+                                      tile_id_bits(num_tiles), bs.sort, false, true, stream);
+        }
         if ((st = check_stage("tile sort", debug, stream))) return st;
         const uint32_t* sorted_tiles = (passes & 1) ? bs.keys_b : bs.keys_a;
         point_list = (passes & 1) ? bs.vals_b : bs.vals_a;
+        StageScope sc(kStageTileRanges, stream);
         launch_tile_ranges(sorted_tiles, gs.counters, (uint32_t)capacity, is.ranges, stream);
         if ((st = check_stage("tile ranges", debug, stream))) return st;
     }
@@ -110,7 +125,10 @@ int bin_and_blend(const adgs_camera* cam, int P, int D_S, bool has_flow, const f
     b.out_semantic = out->semantic;
     b.counters = gs.counters;
     b.capacity = (uint32_t)capacity;
-    launch_blend_forward(b, has_flow, stream);
+    {
+        StageScope sc(kStageBlendFwd, stream);
+        launch_blend_forward(b, has_flow, stream);
+    }
     return check_stage("blend forward", debug, stream);
 }
 
@@ -184,7 +202,10 @@ static int forward_common(const adgs_camera* cam, const adgs_gaussians* g, const
     a.record = reinterpret_cast<float4*>(gs.record);
     a.cov3D = gs.cov3D;
     a.clamped = gs.clamped;
-    launch_preprocess(a, stream);
+    {
+        StageScope sc(kStagePerGaussianFwd, stream);
+        launch_preprocess(a, stream);
+    }
     int st = check_stage("preprocess", cam->debug != 0, stream);
     if (st) return st;
     return bin_and_blend(cam, P, a.D_S, g->flow_points != nullptr, g->semantic, out, radii, gs, binning,
@@ -396,7 +417,10 @@ int adgs_rasterize_backward(const adgs_camera* cam, const adgs_gaussians* g, con
     b.dL_dsemantic_g = grads->dL_dsemantic;
     if (D_S > 1 && !grads->dL_dsemantic) return ADGS_ERR_ARG;
     if (R > 0) {
-        launch_blend_backward(b, g->flow_points != nullptr, stream);
+        {
+            StageScope sc(kStageBlendBwd, stream);
+            launch_blend_backward(b, g->flow_points != nullptr, stream);
+        }
         int st = check_stage("blend backward", debug, stream);
         if (st) return st;
     }
@@ -429,7 +453,10 @@ int adgs_rasterize_backward(const adgs_camera* cam, const adgs_gaussians* g, con
     a.dL_drotations = grads->dL_drotations;
     a.dL_dflow_points = grads->dL_dflow_points;
     a.dL_dsemantic = grads->dL_dsemantic;
-    launch_preprocess_backward(a, stream);
+    {
+        StageScope sc(kStagePerGaussianBwd, stream);
+        launch_preprocess_backward(a, stream);
+    }
     return check_stage("preprocess backward", debug, stream);
 }
 

@@ -17,6 +17,33 @@ int bin_and_blend(const adgs_camera* cam, int P, int D_S, bool has_flow, const f
                   adgs_alloc_fn binning_alloc, void* alloc_user, int64_t capacity, ImageState& is,
                   bool sync_for_count, int* num_rendered, cudaStream_t stream);
 
+// ---- per-stage profiling / launch counting (profile.cu) ------------------------------------------
+enum Stage {
+    kStagePerGaussianFwd = 0,
+    kStageDepthSort,
+    kStageScan,
+    kStageEmit,
+    kStageTileSort,
+    kStageTileRanges,
+    kStageBlendFwd,
+    kStageBlendBwd,
+    kStagePerGaussianBwd,
+    kStageRotationBwd,
+    kStageFills,
+    kNumStages
+};
+
+void count_launch(int n);
+
+struct StageScope {
+    StageScope(int stage, cudaStream_t stream);
+    ~StageScope();
+    int stage_;
+    cudaStream_t stream_;
+    bool active_;
+    int index_ = -1;
+};
+
 const uint32_t* sorted_point_list(const BinningState& bs, int num_tiles);
 const uint32_t* sorted_tile_ids(const BinningState& bs, int num_tiles);
 

@@ -546,6 +546,7 @@ int adgs_trajectory_forward(const adgs_model* model, const adgs_time_basis* basi
     a.out = *out;
     a.render = 0;
     fused_forward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+    count_launch(1);
     return check_stage("trajectory forward", false, stream);
 }
 
@@ -593,7 +594,11 @@ int adgs_render_forward(const adgs_camera* cam, const adgs_model* model, const a
     a.clamped = gs.clamped;
     char* sc = saved;
     carve(sc, a.saved, (size_t)N * 3);
-    fused_forward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+    {
+        StageScope sc(kStagePerGaussianFwd, stream);
+        fused_forward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+        count_launch(1);
+    }
     st = check_stage("fused forward", cam->debug != 0, stream);
     if (st) return st;
     int R = 0;
@@ -658,12 +663,16 @@ int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const 
     b.dL_dcolor = dpix->dL_dcolor;
     b.dL_ddepth = dpix->dL_ddepth;
     b.dL_dflow = has_flow ? dpix->dL_dflow : nullptr;
-    b.dL_dsemantic = nullptr;  // the object mask is a constant: no gradient flows into it
+    // the object mask itself is a constant, but its image cotangent still reaches alpha (backward.cu:597-603)
+    b.dL_dsemantic = render_objmask ? dpix->dL_dsemantic : nullptr;
     b.dL_dopacity = dpix->dL_dopacity;
     b.grad_record = grad_record;
     b.dL_dsemantic_g = nullptr;
     if (capacity > 0) {
-        launch_blend_backward(b, has_flow, stream);
+        {
+            StageScope sc(kStageBlendBwd, stream);
+            launch_blend_backward(b, has_flow, stream);
+        }
         if ((st = check_stage("blend backward", debug, stream))) return st;
     }
 
@@ -695,13 +704,20 @@ int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const 
     a.dL_dmeans2D = dL_dmeans2D;
     a.dq_scratch = dq_scratch;
     a.bg_scratch = bg_scratch;
-    fused_backward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+    {
+        StageScope sc(kStagePerGaussianBwd, stream);
+        fused_backward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+        count_launch(1);
+    }
     if ((st = check_stage("fused backward", debug, stream))) return st;
     if (No > 0) {
+        StageScope sc(kStageRotationBwd, stream);
         rotation_backward_kernel<<<(No + 127) / 128, 128, 0, stream>>>(a);
-        if ((st = check_stage("rotation backward", debug, stream))) return st;
+        count_launch(1);
     }
+    if ((st = check_stage("rotation backward", debug, stream))) return st;
     if (grads->background_deform && basis->background.n_cols > 0) {
+        count_launch(1);
         background_finalize_kernel<<<1, 128, 0, stream>>>(a);
         if ((st = check_stage("background finalize", debug, stream))) return st;
     }

@@ -3,6 +3,7 @@
 #include "sort.cuh"
 
 namespace adgs {
+void count_launch(int n);
 namespace {
 
 __device__ __forceinline__ int effective_sh_degree(int deg, int M)
@@ -306,12 +307,14 @@ __global__ void __launch_bounds__(256) preprocess_bwd_aos_kernel(const Preproces
 void launch_preprocess(const PreprocessArgs& a, cudaStream_t stream)
 {
     if (a.P <= 0) return;
+    count_launch(1);
     preprocess_aos_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(a);
 }
 
 void launch_preprocess_backward(const PreprocessBwdArgs& a, cudaStream_t stream)
 {
     if (a.P <= 0) return;
+    count_launch(1);
     preprocess_bwd_aos_kernel<<<(a.P + 255) / 256, 256, 0, stream>>>(a);
 }
 
@@ -319,6 +322,7 @@ void launch_mark_visible(int P, const float* means3D, const float* view, const f
                          cudaStream_t stream)
 {
     if (P <= 0) return;
+    count_launch(1);
     mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, view, proj, present);
 }
 
@@ -327,6 +331,7 @@ void launch_emit(int P, const uint32_t* depth_order, const uint32_t* point_offse
                  uint32_t capacity, uint32_t* counters, cudaStream_t stream)
 {
     if (P <= 0) return;
+    count_launch(1);
     emit_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, depth_order, point_offsets, tiles_touched, record, radii,
                                                      grid_x, grid_y, keys, vals, capacity, counters);
 }
@@ -338,6 +343,7 @@ void launch_tile_ranges(const uint32_t* sorted_tiles, const uint32_t* counters, 
     size_t want = ((size_t)capacity + 255) / 256;
     int grid = (int)min((size_t)sms * 8, want);
     if (grid < 1) grid = 1;
+    count_launch(1);
     tile_ranges_kernel<<<grid, 256, 0, stream>>>(sorted_tiles, counters, capacity, ranges);
 }
 

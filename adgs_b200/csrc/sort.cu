@@ -10,6 +10,7 @@
 #include "sort.cuh"
 
 namespace adgs {
+void count_launch(int n);
 
 const DeviceInfo& device_info()
 {
@@ -301,6 +302,7 @@ int sort_pairs_async(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint3
     {
         int grid = (int)min((size_t)sms * 4, (n_max + 256 * 16 - 1) / (256 * 16));
         if (grid < 1) grid = 1;
+        count_launch(1);
         radix_histogram_kernel<<<grid, 256, 0, stream>>>(keys_a, (uint32_t)n_max, d_n, begin_bit, end_bit, ws.hist);
     }
     uint32_t* kin = keys_a;
@@ -316,9 +318,11 @@ int sort_pairs_async(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint3
         uint32_t* status = ws.status + (size_t)p * ws.tiles * kRadix;
         uint32_t* ticket = ws.tickets + p;
         if (p == 0 && iota_values) {
+            count_launch(1);
             onesweep_pass_kernel<true><<<grid, kSortThreads, 0, stream>>>(kin, nullptr, kout, vout, (uint32_t)n_max,
                                                                           d_n, shift, mask, hist, status, ticket);
         } else {
+            count_launch(1);
             onesweep_pass_kernel<false><<<grid, kSortThreads, 0, stream>>>(kin, vin, kout, vout, (uint32_t)n_max, d_n,
                                                                            shift, mask, hist, status, ticket);
         }
@@ -340,6 +344,7 @@ void inclusive_scan_gather_async(const uint32_t* in, const uint32_t* order, uint
     const int sms = device_info().sm_count;
     int grid = (int)min((size_t)sms * 4, tiles);
     if (grid < 1) grid = 1;
+    count_launch(1);
     scan_gather_kernel<<<grid, kScanThreads, 0, stream>>>(in, order, out, (uint32_t)n, status, total_out);
 }
 

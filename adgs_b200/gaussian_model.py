@@ -294,6 +294,7 @@ class GaussianModel(nn.Module):
 
     def _note_num_rendered(self, R: int):
         """Sync-free binning: keep the arena 30 % above the largest num_rendered seen so far."""
+        self._last_num_rendered = int(R)
         self._binning_capacity = max(self._binning_capacity, int(1.3 * R) + 65536)
 
     def time_basis(self, t, flow_t=None) -> L.TimeBasis:

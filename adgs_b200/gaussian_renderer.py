@@ -137,7 +137,8 @@ class _FusedRender(torch.autograd.Function):
                 gm = model.c_model_from(grads, with_time=False)
                 cot = [None if g is None else g.contiguous() for g in (g_color, g_depth, g_flow, g_sem, g_opacity)]
                 ig = L.ImageGrads(dL_dcolor=L.ptr(cot[0]), dL_ddepth=L.ptr(cot[1]), dL_dflow=L.ptr(cot[2]),
-                                  dL_dsemantic=None, dL_dopacity=L.ptr(cot[4]))
+                                  dL_dsemantic=L.ptr(cot[3]) if ctx.render_objmask else None,
+                                  dL_dopacity=L.ptr(cot[4]))
                 scratch = torch.empty((lib.adgs_render_scratch_bytes(N, model.n_obj),), dtype=torch.uint8, device=dev)
                 st = lib.adgs_render_backward(C.byref(cam), C.byref(cm), C.byref(tb), int(ctx.render_objmask),
                                               L.ptr(radii), L.ptr(geom), L.ptr(binning), int(ctx.capacity), L.ptr(img),

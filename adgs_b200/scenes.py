@@ -104,3 +104,46 @@ def activated_inputs(cloud, device="cuda", requires_grad=False):
         for v in out.values():
             v.requires_grad_(True)
     return out
+
+
+BENCH_ORDER_ARGS = {  # kitti-75 / waymo style with 32 control points: 96 frames // 3
+    'xyz': [32, 5, 0, 6, 0, 0],
+    'rotation': [0, 0, 0, 0, 32, 5],
+    'shs': [0, 0, 0, 6, 0, 0],
+    'background': [32, 5, 0, 6, 0, 0],
+}
+
+
+def random_model_tensors(n_scene, n_obj, order_args, cloud, seed=0, device="cuda", deform_scale=1e-2,
+                         time_sigma=1.0 / 96.0):
+    """Seeded parameters in the REFERENCE's tensor layout and naming (the shapes of
+    scene/gaussian_model.py:create_from_pcd, :285-328): Gaussians [0, n_scene) of `cloud` are scene,
+    the rest objects. Deformation parameters ~ U(-1,1)*deform_scale, gs_time ~ U(0,1),
+    gs_time_sigma = log(time_sigma)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    n = n_scene + n_obj
+
+    def num(a):
+        return a[0] + a[2] + 2 * a[3] + a[4]
+
+    def U(*shape):
+        return ((torch.rand(*shape, generator=g) * 2 - 1) * deform_scale).to(device)
+
+    t = {k: torch.tensor(cloud[k], dtype=torch.float32, device=device) for k in
+         ("xyz", "scaling_raw", "rotation_raw", "opacity_raw", "shs")}
+    out = dict(
+        scene_xyz=t["xyz"][:n_scene], obj_xyz=t["xyz"][n_scene:],
+        scene_shs_dc=t["shs"][:n_scene, 0:1], obj_shs_dc=t["shs"][n_scene:, 0:1],
+        scene_shs_rest=t["shs"][:n_scene, 1:], obj_shs_rest=t["shs"][n_scene:, 1:],
+        scene_scaling=t["scaling_raw"][:n_scene], obj_scaling=t["scaling_raw"][n_scene:],
+        scene_rotation=t["rotation_raw"][:n_scene], obj_rotation=t["rotation_raw"][n_scene:],
+        scene_opacity=t["opacity_raw"][:n_scene], obj_opacity=t["opacity_raw"][n_scene:],
+        xyz_deform_param=U(n_obj, 3, num(order_args['xyz'])),
+        rotation_deform_param=U(n_obj, 4, num(order_args['rotation'])),
+        shs_deform_param_scene=U(n_scene, 3, num(order_args['shs'])),
+        shs_deform_param_obj=U(n_obj, 3, num(order_args['shs'])),
+        background_deform_param=U(1, 3, num(order_args['background'])),
+        gs_time=torch.rand(n_obj, 1, generator=g).to(device),
+        gs_time_sigma=torch.full((n_obj, 2), math.log(time_sigma), dtype=torch.float32, device=device),
+    )
+    return {k: v.contiguous() for k, v in out.items()}

@@ -1,0 +1,480 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the AD-GS hot path (BASELINE.json: fwd+bwd Mpix/s and
+Gaussians/s, % of HBM roofline).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one forward+backward of gaussian_renderer.render() per rank (trajectory at t and at
+flow_time -> projection -> binning -> blend -> full backward to every parameter gradient), with
+fixed seeded cotangents on the five output images so that no loss kernels are timed
+(SURVEY.md section 8d). N > 1: launched by torchrun, one rank per GPU; each rank renders its own
+view of an N-view batch and the parameter gradients are summed by one NCCL all-reduce over a flat
+buffer inside the timed step (weak scaling).
+
+The JSON line carries `value` (inputs resident in HBM), `e2e` (same metric through the public
+API with the per-step host inputs copied from pinned memory and a device->host read of a
+metric), `roofline` (dominant kernel, CUDA-event timed through the library's stage hooks),
+`cpu_baseline` (reference trajectory+SH path on the host cores, rank 0, N=1 only), `clocks`,
+`gpu_launches`.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: KITTI-MOT-shaped frame, 1M Gaussians (25 % objects, 32 control points)
+    "kitti-375x1242-1M": dict(W=1242, H=375, n=1_000_000, obj_frac=0.25, median_radius_px=3.0),
+    # smaller variants for quick checks
+    "kitti-375x1242-200k": dict(W=1242, H=375, n=200_000, obj_frac=0.25, median_radius_px=3.0),
+    "tiny": dict(W=320, H=192, n=20_000, obj_frac=0.25, median_radius_px=3.0),
+}
+T_CAMERA, T_FLOW = 0.37, 0.41
+METRIC = "fwd+bwd Mpix/s"
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(n_scene, n_obj, R, px):
+    """B_alg = N_s*1220 + N_o*2790 + R*404 + Px*84 per view, and its split by stage."""
+    n = n_scene + n_obj
+    stages = {
+        "per_gaussian_forward": n_scene * 496 + n_obj * 1020,
+        "binning": n * 24 + R * 172,                       # scan + emit + sort + ranges
+        "blend_forward": R * 60 + px * 40,
+        "blend_backward": R * 172 + px * 44,
+        "per_gaussian_backward": n_scene * 700 + n_obj * 1748,
+    }
+    total = n_scene * 1220 + n_obj * 2790 + R * 404 + px * 84
+    return total, stages
+
+
+def build_ours(wl, device, seed=0):
+    import torch
+    from adgs_b200 import scenes
+    from adgs_b200.gaussian_model import GaussianModel
+    n, n_obj = wl["n"], int(wl["n"] * wl["obj_frac"])
+    n_scene = n - n_obj
+    cam0 = scenes.make_camera(wl["W"], wl["H"], 90.0, time=T_CAMERA)
+    cloud = scenes.random_cloud(n, cam0, seed=seed, median_radius_px=wl["median_radius_px"])
+    tensors = scenes.random_model_tensors(n_scene, n_obj, scenes.BENCH_ORDER_ARGS, cloud, seed=seed + 1, device=device)
+    model = GaussianModel.from_reference(tensors, scenes.BENCH_ORDER_ARGS, device=device)
+    del tensors
+    torch.cuda.empty_cache()
+    return model, n_scene, n_obj
+
+
+def view_for_rank(wl, rank, device):
+    """8-view batch = 4 timesteps x 2 cameras; rank r renders view r."""
+    from adgs_b200 import scenes
+    yaw = 0.0 if rank % 2 == 0 else 8.0
+    t = T_CAMERA + 0.05 * (rank // 2)
+    cam = scenes.make_camera(wl["W"], wl["H"], 90.0, yaw_deg=yaw, time=t, device=device)
+    return cam, t, t + (T_FLOW - T_CAMERA)
+
+
+def make_cotangents(wl, device, seed=7, pinned=False):
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    H, W = wl["H"], wl["W"]
+    host = {k: torch.randn(c, H, W, generator=g) for k, c in (("color", 3), ("depth", 1), ("opacity", 1), ("flow", 3),
+                                                             ("semantic", 1))}
+    if pinned:
+        return {k: v.pin_memory() for k, v in host.items()}
+    return {k: v.to(device) for k, v in host.items()}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from adgs_b200 import _lib as L
+    from adgs_b200.gaussian_renderer import render
+    from adgs_b200.parallel import MultiViewStep
+
+    rank, world, local = dist_env()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torchrun (one rank per GPU)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = L.load()
+    wl = WORKLOADS[args.workload]
+    model, n_scene, n_obj = build_ours(wl, device)
+    cam, t, flow_t = view_for_rank(wl, rank, device)
+    cot = make_cotangents(wl, device)
+    pipe = SimpleNamespace(inv_depth=True, debug=False, sync_free=True)
+    flow_pkg = [flow_t, None, None, None, None, None]
+    params = model.hot_parameters()
+    px = wl["W"] * wl["H"]
+
+    def outputs_and_cotangents(res, c):
+        return ((res["render"], res["depth"], res["img_opacity"], res["img_flow"], res["img_semantic"]),
+                (c["color"], c["depth"][0], c["opacity"][0], c["flow"], c["semantic"]))
+
+    mv = MultiViewStep(model) if world > 1 else None
+
+    def step():
+        if mv is None:
+            for p in params:
+                p.grad = None
+            res = render(cam, model, None, pipe, flow_pkg=flow_pkg, render_objmask=True)
+            outs, cots = outputs_and_cotangents(res, cot)
+            torch.autograd.backward(outs, cots)
+            return res
+        views = [None] * world   # this rank's shard is exactly its own view
+        views[rank] = (cam, flow_pkg)
+        mv.run(views, lambda v: render(v[0], model, None, pipe, flow_pkg=v[1], render_objmask=True),
+               lambda v, r: outputs_and_cotangents(r, cot), reduce_stats=False)
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.adgs_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (lib.adgs_launch_count() - launches0) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([ms], device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    mpix = world * px / (ms * 1e-3) / 1e6
+    gauss = world * wl["n"] / (ms * 1e-3)
+
+    # ---- roofline: per-stage CUDA events through the library hooks (rank 0) ------------------------
+    roof, stage_ms, step_roof = None, None, None
+    R = int(getattr(model, "_last_num_rendered", 0))
+    if rank == 0:
+        import ctypes as C
+        ns = lib.adgs_profile_num_stages()
+        ms_buf = (C.c_float * ns)()
+        cnt_buf = (C.c_int32 * ns)()
+        torch.cuda.synchronize()
+        lib.adgs_profile_begin()
+        prof_steps = max(3, min(args.steps, 10))
+        for _ in range(prof_steps):
+            for p in params:
+                p.grad = None
+            res = render(cam, model, None, pipe, flow_pkg=flow_pkg, render_objmask=True)
+            outs, cots = outputs_and_cotangents(res, cot)
+            torch.autograd.backward(outs, cots)
+        torch.cuda.synchronize()
+        lib.adgs_profile_end(ms_buf, cnt_buf)
+        stage_ms = {lib.adgs_profile_stage_name(i).decode(): ms_buf[i] / prof_steps for i in range(ns)}
+        R = int(getattr(model, "_last_num_rendered", R))
+        total_b, per_stage = algorithmic_bytes(n_scene, n_obj, R, px)
+        peak, peak_src = measured_hbm_peak()
+        kernel_stages = {k: stage_ms[k] for k in ("per_gaussian_forward", "blend_forward", "blend_backward",
+                                                   "per_gaussian_backward")}
+        top = max(kernel_stages, key=kernel_stages.get)
+        ach = per_stage[top] / (kernel_stages[top] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(top)
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": per_stage[top], "kernel_ms": round(kernel_stages[top], 4),
+                "note": "blend kernels are FP32/SFU-issue bound, not HBM bound (DESIGN.md); reported against HBM per BASELINE"}
+        step_ach = total_b / (ms * 1e-3) / 1e9
+        step_roof = {"algorithmic_bytes_per_view": total_b, "achieved_GBps": round(step_ach, 1),
+                     "frac_of_hbm_peak": round(step_ach / peak, 4), "num_rendered": R}
+
+    # ---- e2e: host buffers in, host metric out, every step ---------------------------------------------
+    host_cot = make_cotangents(wl, device, pinned=True)
+    host_cam = {k: getattr(cam, k).cpu().pin_memory() for k in ("world_view_transform", "full_proj_transform",
+                                                                "camera_center")}
+    h2d = sum(v.numel() * 4 for v in host_cot.values()) + sum(v.numel() * 4 for v in host_cam.values())
+    d2h = 4
+
+    def e2e_step():
+        c = {k: v.to(device, non_blocking=True) for k, v in host_cot.items()}
+        vc = cam._replace(**{k: v.to(device, non_blocking=True) for k, v in host_cam.items()})
+        for p in params:
+            p.grad = None
+        res = render(vc, model, None, pipe, flow_pkg=flow_pkg, render_objmask=True)
+        outs, cots = outputs_and_cotangents(res, c)
+        torch.autograd.backward(outs, cots)
+        if mv is not None:
+            bucket = mv.bucket
+            v = bucket.views()
+            for k, p in zip(mv.names, params):
+                v[k].copy_(p.grad)
+            bucket.all_reduce()
+        return float(res["img_opacity"].mean().item())   # device -> host read of a metric
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        tt = torch.tensor([ms_e2e], device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tt.item())
+    e2e = {"value": round(world * px / (ms_e2e * 1e-3) / 1e6, 2), "unit": "Mpix/s", "ms_per_step": round(ms_e2e, 4),
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(mpix, 2), "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "views_per_step": world, "image": [wl["H"], wl["W"]],
+                       "gaussians": wl["n"], "object_fraction": wl["obj_frac"], "control_points": 32,
+                       "bspline_order": 5, "fourier_terms": 6, "sh_degree": 3, "flow": True, "objmask": True,
+                       "inv_depth": True, "l2": "inputs (>1.5 GB of parameters per step) exceed the 126 MB L2",
+                       "parallelism": f"views sharded over {world} rank(s), flat-buffer NCCL all-reduce of parameter gradients"},
+            "gaussians_per_s": round(gauss, 1),
+            "e2e": e2e, "gpu_launches": round(launches, 1), "clocks": clocks,
+            "roofline": roof, "step_roofline": step_roof, "stage_ms": {k: round(v, 4) for k, v in (stage_ms or {}).items()},
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(budget_s=15.0):
+    """BASELINE config 1: the reference's B-spline trajectory + SH evaluation (no rasterizer) on CPU
+    torch, 100k Gaussians (all objects), 32 control points, forward+backward, all host threads.
+    This is the oracle port (oracle/trajectory_oracle.py) being TIMED AS A BASELINE, nothing more."""
+    import torch
+    from oracle import trajectory_oracle as TO
+    from adgs_b200 import scenes
+    n = 100_000
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ref = TO.random_reference_model(0, n, scenes.BENCH_ORDER_ARGS, seed=0, device="cpu", requires_grad=True)
+    campos = torch.zeros(3)
+    params = [getattr(ref, f) for f in ref.trainable()]
+
+    def it():
+        for p in params:
+            p.grad = None
+        flow = ref.get_deformed_xyz(T_FLOW)
+        pkg = ref.get_deformed_pkg(T_CAMERA)
+        rgb = TO.sh_colors(pkg["shs"], pkg["xyz"], campos, 3)
+        (rgb.sum() + flow.sum() + pkg["opacity"].sum() + pkg["rotation"].sum() + ref.get_scaling().sum()).backward()
+
+    it()
+    t0 = time.perf_counter()
+    k = 0
+    while True:
+        it()
+        k += 1
+        if time.perf_counter() - t0 > budget_s or k >= 50:
+            break
+    dt = (time.perf_counter() - t0) / k
+    return {"value": round(n / dt, 1), "unit": "Gaussians/s (trajectory + SH colour, fwd+bwd, no rasterizer)",
+            "cores": cores, "kind": "port", "ms_per_iter": round(dt * 1e3, 2),
+            "sample": f"BASELINE configs[0]: {n} object Gaussians, 32 control points, k=5, F=6, SH degree 3; {k} iterations"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own implementation of the path -- its UNMODIFIED CUDA
+    rasterizer (oracle/_ref, compiled from /root/reference) driven by the torch trajectory exactly as
+    gaussian_renderer.render() drives it -- on the same workload, metric and timing harness.
+    (The reference has no CPU rasterizer; if neither a GPU nor oracle/_ref is available, the numpy
+    oracle port is timed on a bounded sample instead.)"""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    import torch
+    from oracle import ref_module as REF
+    wl = WORKLOADS[args.workload]
+    px = wl["W"] * wl["H"]
+    cores = os.cpu_count() or 1
+    if torch.cuda.is_available() and REF.available():
+        from oracle import trajectory_oracle as TO
+        from oracle.ref_pipeline import reference_render
+        from adgs_b200 import scenes
+        torch.cuda.set_device(local)
+        device = torch.device("cuda", local)
+        n, n_obj = wl["n"], int(wl["n"] * wl["obj_frac"])
+        n_scene = n - n_obj
+        cam0 = scenes.make_camera(wl["W"], wl["H"], 90.0, time=T_CAMERA)
+        cloud = scenes.random_cloud(n, cam0, seed=0, median_radius_px=wl["median_radius_px"])
+        tensors = scenes.random_model_tensors(n_scene, n_obj, scenes.BENCH_ORDER_ARGS, cloud, seed=1, device=device)
+        for k, v in tensors.items():
+            if k != "gs_time":
+                v.requires_grad_(True)
+        ref = TO.ReferenceModel(scenes.BENCH_ORDER_ARGS, True, **tensors)
+        cam, t, flow_t = view_for_rank(wl, 0, device)
+        c = dict(cam=cam, W=wl["W"], H=wl["H"], n=n, background=torch.zeros(3, device=device),
+                 tan_fovx=math.tan(cam.FoVx * 0.5), tan_fovy=math.tan(cam.FoVy * 0.5), degree=3, inv_depth=True)
+        cot = make_cotangents(wl, device)
+        params = [getattr(ref, f) for f in ref.trainable()]
+
+        def step():
+            for p in params:
+                p.grad = None
+            (color, radii, depth, opac, flow, sem), _ = reference_render(ref, c, t, flow_t, REF)
+            torch.autograd.backward((color, depth, opac, flow, sem),
+                                    (cot["color"], cot["depth"], cot["opacity"], cot["flow"], cot["semantic"]))
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        value = px / (ms * 1e-3) / 1e6
+        kind, sample = "reference", ("unmodified reference CUDA rasterizer (oracle/_ref) + torch trajectory on the GPU, "
+                                     "full workload; runs on the GPU because the reference has no CPU rasterizer")
+    else:
+        from oracle import raster_oracle as O
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers as Hh
+        c = Hh.make_case(n=2000, W=96, H=64, seed=1, device="cpu")
+        s = Hh.oracle_settings(c)
+        n_ = Hh.to_np
+        cot = Hh.cotangents(c, device="cpu")
+        t0 = time.perf_counter()
+        k = 0
+        while k < args.steps and time.perf_counter() - t0 < 60:
+            out, st = O.rasterize_forward(s, n_(c["means3D"]), n_(c["opacity"]), n_(c["scales"]), n_(c["rotations"]),
+                                          None, n_(c["sh"]), None, n_(c["flow_points"]), n_(c["semantic"]))
+            O.rasterize_backward(s, st, out, n_(c["means3D"]), n_(cot["color"]), n_(cot["depth"]), n_(cot["flow"]),
+                                 n_(cot["semantic"]), n_(cot["opacity"]), n_(c["scales"]), n_(c["rotations"]), None,
+                                 n_(c["sh"]), n_(c["flow_points"]), n_(c["semantic"]))
+            k += 1
+        ms = (time.perf_counter() - t0) / max(k, 1) * 1e3
+        value = 96 * 64 / (ms * 1e-3) / 1e6
+        kind, sample = "port", "numpy oracle port on the host, bounded sample: 2000 Gaussians at 96x64 (rasterizer only)"
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mpix/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload},
+            "cpu_baseline": {"value": round(value, 3), "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": round(value, 3), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="kitti-375x1242-1M", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -331,6 +331,18 @@ ADGS_API int adgs_render_backward(const adgs_camera* cam, const adgs_model* mode
                          adgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): cumulative number of kernels launched by the library, and
+ * optional CUDA-event timing of each pipeline stage on the caller's stream.
+ * adgs_profile_begin() arms it; adgs_profile_end() synchronises the recorded events and returns,
+ * per stage, the summed milliseconds and the number of timed scopes.
+ * ---------------------------------------------------------------------------------------- */
+ADGS_API unsigned long long adgs_launch_count(void);
+ADGS_API int adgs_profile_begin(void);
+ADGS_API int adgs_profile_num_stages(void);
+ADGS_API const char* adgs_profile_stage_name(int stage);
+ADGS_API int adgs_profile_end(float* ms_per_stage, int32_t* scopes_per_stage);
+
+/* ------------------------------------------------------------------------------------------
  * simple-knn: replaces SimpleKNN::knn / distCUDA2 (KNN/simple_knn.h:18, KNN/spatial.cu:16-26):
  * mean squared distance to the 3 nearest neighbours of every point.
  * ---------------------------------------------------------------------------------------- */

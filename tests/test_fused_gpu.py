@@ -30,35 +30,6 @@ ORDER_SETS = {
 }
 
 
-class _RefRasterize(torch.autograd.Function):
-    """autograd shell around a rasterizer backend with the reference's _C signatures."""
-
-    @staticmethod
-    def forward(ctx, backend, c, means3D, opacity, scales, rotations, sh, flow_points, semantic):
-        cam = c["cam"]
-        args = (c["background"], means3D, torch.Tensor([]), opacity, scales, rotations, 1.0, torch.Tensor([]),
-                cam.world_view_transform, cam.full_proj_transform, c["tan_fovx"], c["tan_fovy"], c["H"], c["W"], sh,
-                flow_points, semantic, c["degree"], cam.camera_center, False, c["inv_depth"], False)
-        out = backend.rasterize_gaussians(*args)
-        ctx.backend, ctx.c, ctx.out = backend, c, out
-        ctx.save_for_backward(means3D, opacity, scales, rotations, sh, flow_points, semantic)
-        return out[1], out[4], out[2], out[3], out[8], out[9]
-
-    @staticmethod
-    def backward(ctx, g_color, g_radii, g_depth, g_opacity, g_flow, g_sem):
-        means3D, opacity, scales, rotations, sh, flow_points, semantic = ctx.saved_tensors
-        c, out, cam = ctx.c, ctx.out, ctx.c["cam"]
-        args = (c["background"], means3D, out[4], torch.Tensor([]), scales, rotations, 1.0, torch.Tensor([]),
-                cam.world_view_transform, cam.full_proj_transform, c["tan_fovx"], c["tan_fovy"], g_color, g_depth,
-                g_flow, g_sem, semantic, flow_points, sh, c["degree"], cam.camera_center, out[5], out[0], out[6],
-                out[7], out[3], g_opacity, c["inv_depth"], False)
-        if ctx.backend is Hh.OURS:
-            g = ctx.backend.rasterize_gaussians_backward(*args, opacities=opacity)
-        else:
-            g = ctx.backend.rasterize_gaussians_backward(*args)
-        return None, None, g[3], g[2], g[6], g[7], g[5], g[8], None
-
-
 def _backend():
     from oracle import ref_module as REF
     return REF if REF.available() else Hh.OURS
@@ -80,11 +51,8 @@ def _scene(n_scene, n_obj, order_key, W=160, H=96, seed=0, deform_scale=1e-2, fr
 
 
 def _reference_render(ref, c, t, flow_t, backend):
-    pkg = ref.get_deformed_pkg(t)
-    flow = ref.get_deformed_xyz(flow_t)
-    sem = ref.get_obj_mask().float()[..., None]
-    return _RefRasterize.apply(backend, c, pkg['xyz'], pkg['opacity'], ref.get_scaling(), pkg['rotation'], pkg['shs'],
-                               flow, sem), pkg
+    from oracle.ref_pipeline import reference_render
+    return reference_render(ref, c, t, flow_t, backend)
 
 
 @pytest.mark.parametrize("order_key,deform_scale", [("kitti75", 1e-2), ("kitti75", 1e-5), ("waymo", 3e-2),
