@@ -94,7 +94,7 @@ def test_fused_render_matches_reference_pipeline(order_key, deform_scale):
     for f in ref.trainable():
         want = getattr(ref, f).grad
         if want is None:          # e.g. obj_rotation unused in quaternion-spline mode
-            assert g[f].abs().max().item() == 0.0, f
+            assert g[f].numel() == 0 or g[f].abs().max().item() == 0.0, f
             continue
         assert g[f].shape == want.shape, f
         if want.numel():
