@@ -40,9 +40,12 @@ struct BlendBwdArgs {
 };
 
 // Conservative test: can ANY pixel centre of the rectangle [X0,X1]x[Y0,Y1] receive
-// alpha >= 1/255 from this splat? thresh = -log(255*opacity) (power must reach it).
-// The quadratic power(d) = -0.5*(A dx^2 + C dy^2) - B dx dy attains its maximum over the
-// rectangle either at d = 0 (inside) or on the boundary; each edge is a 1-D quadratic.
+// alpha >= 1/255 from this splat? thresh = -log(255*opacity): power(d) must reach it.
+// power(d) = -0.5*(A dx^2 + C dy^2) - B dx dy is concave for a positive-definite conic, so its
+// maximum over the rectangle is 0 if the mean lies inside, and otherwise sits on an edge that
+// FACES the mean (the segment from the mean to any better interior point would cross such an
+// edge inside the same super-level set). At most two edges face the mean; on each the maximiser
+// is the clamped vertex of a 1-D parabola. Non-definite conics (numerical garbage) are kept.
 __device__ __forceinline__ float power_at(float A, float B, float C, float dx, float dy)
 {
     return -0.5f * (A * dx * dx + C * dy * dy) - B * dx * dy;
@@ -52,34 +55,26 @@ __device__ __forceinline__ bool splat_may_touch_rect(float mx, float my, float A
                                                      float X0, float Y0, float X1, float Y1)
 {
     if (!(thresh <= 0.01f)) return false;  // opacity < 1/255 (or non-positive): alpha can never pass
-    // d = mean - pixel
+    if (!(A > 0.f && C > 0.f && A * C - B * B > 0.f)) return true;
+    // d = mean - pixel; nearest rectangle coordinates to the mean
+    const float dx0 = mx - fminf(fmaxf(mx, X0), X1);  // 0 when the mean is inside the x-range
+    const float dy0 = my - fminf(fmaxf(my, Y0), Y1);
+    if (dx0 == 0.f && dy0 == 0.f) return true;
     const float dx_lo = mx - X1, dx_hi = mx - X0;
     const float dy_lo = my - Y1, dy_hi = my - Y0;
-    if (dx_lo <= 0.f && dx_hi >= 0.f && dy_lo <= 0.f && dy_hi >= 0.f) return true;
-    float best = power_at(A, B, C, dx_lo, dy_lo);
-    best = fmaxf(best, power_at(A, B, C, dx_lo, dy_hi));
-    best = fmaxf(best, power_at(A, B, C, dx_hi, dy_lo));
-    best = fmaxf(best, power_at(A, B, C, dx_hi, dy_hi));
-    if (C > 0.f) {
-        const float inv = 1.f / C;
-        float v = fminf(fmaxf(-B * dx_lo * inv, dy_lo), dy_hi);
-        best = fmaxf(best, power_at(A, B, C, dx_lo, v));
-        v = fminf(fmaxf(-B * dx_hi * inv, dy_lo), dy_hi);
-        best = fmaxf(best, power_at(A, B, C, dx_hi, v));
+    float best = -3.0e38f;
+    if (dx0 != 0.f) {  // vertical edge facing the mean: dx fixed, dy free in [dy_lo, dy_hi]
+        const float v = fminf(fmaxf(__fdividef(-B * dx0, C), dy_lo), dy_hi);
+        best = power_at(A, B, C, dx0, v);
     }
-    if (A > 0.f) {
-        const float inv = 1.f / A;
-        float v = fminf(fmaxf(-B * dy_lo * inv, dx_lo), dx_hi);
-        best = fmaxf(best, power_at(A, B, C, v, dy_lo));
-        v = fminf(fmaxf(-B * dy_hi * inv, dx_lo), dx_hi);
-        best = fmaxf(best, power_at(A, B, C, v, dy_hi));
+    if (dy0 != 0.f) {  // horizontal edge facing the mean
+        const float v = fminf(fmaxf(__fdividef(-B * dy0, A), dx_lo), dx_hi);
+        best = fmaxf(best, power_at(A, B, C, v, dy0));
     }
-    // rounding slack: covers the evaluation error of both this test and the per-pixel formula
+    // rounding slack: covers the evaluation error of this test and of the per-pixel formula
     const float dxm = fmaxf(fabsf(dx_lo), fabsf(dx_hi)), dym = fmaxf(fabsf(dy_lo), fabsf(dy_hi));
-    const float mag = 0.5f * (fabsf(A) * dxm * dxm + fabsf(C) * dym * dym) + fabsf(B) * dxm * dym;
-    const float eps = 0.01f + 2e-6f * mag;
-    // NaNs compare false -> keep (never skip on garbage)
-    return !(best < thresh - eps);
+    const float eps = 0.01f + 2e-6f * (A * dxm * dxm + C * dym * dym);
+    return !(best < thresh - eps);  // NaN compares false -> keep
 }
 
 void launch_blend_forward(const BlendFwdArgs& a, bool has_flow, cudaStream_t stream);

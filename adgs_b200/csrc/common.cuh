@@ -18,7 +18,8 @@
 #define ADGS_GRAD_FLOATS 16 /* packed per-Gaussian blend gradient record, 64 B */
 
 // Record layout (floats): 0 x, 1 y, 2 conic.x, 3 conic.y, 4 conic.z, 5 opacity, 6..8 rgb,
-// 9 depth feature (depth or 1/(depth+1e-7)), 10..12 flow point, 13 semantic[0], 14 depth, 15 -
+// 9 depth feature (depth or 1/(depth+1e-7)), 10..12 flow point, 13 semantic[0], 14 depth,
+// 15 cull threshold -log(255*opacity) (1e30 if opacity <= 0)
 // Gradient record layout: 0,1 dmean2D  2,3,4 dconic(x,y,w)  5 dopacity  6..8 dcolor
 // 9 ddepthfeat  10..12 dflow  13 dsemantic[0]
 

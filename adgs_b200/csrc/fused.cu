@@ -99,7 +99,7 @@ __device__ __forceinline__ float4 object_rotation_raw(const adgs_model& m, const
     return q;
 }
 
-__global__ void __launch_bounds__(256) fused_forward_kernel(const __grid_constant__ FusedFwdArgs a)
+__global__ void __launch_bounds__(256, 3) fused_forward_kernel(const __grid_constant__ FusedFwdArgs a)
 {
     __shared__ CamSmem cam;
     __shared__ float s_bg[6];
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) fused_forward_kernel(const __grid_constan
     rec[0] = make_float4(sg.px, sg.py, sg.conic_x, sg.conic_y);
     rec[1] = make_float4(sg.conic_z, op, rgb[0], rgb[1]);
     rec[2] = make_float4(rgb[2], dfeat, flow ? xf[0] : 0.f, flow ? xf[1] : 0.f);
-    rec[3] = make_float4(flow ? xf[2] : 0.f, sem0, sg.depth, 0.f);
+    rec[3] = make_float4(flow ? xf[2] : 0.f, sem0, sg.depth, op > 0.f ? -__logf(255.f * op) : 1e30f);
     a.radii[g] = sg.radius;
     a.tiles_touched[g] = sg.tiles;
     a.depth_keys[g] = __float_as_uint(sg.depth);
@@ -282,7 +282,7 @@ struct FusedBwdArgs {
     float* bg_scratch;   // 6 floats: sum dxyz_t, sum dflow
 };
 
-__global__ void __launch_bounds__(256) fused_backward_kernel(const __grid_constant__ FusedBwdArgs a)
+__global__ void __launch_bounds__(256, 2) fused_backward_kernel(const __grid_constant__ FusedBwdArgs a)
 {
     __shared__ CamSmem cam;
     __shared__ float s_wshs[ADGS_MAX_TERMS * 2];  // dense SH-deform weights per column
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(256) fused_backward_kernel(const __grid_consta
 }
 
 // Object rotation chain: normalised quaternion gradient -> static quaternion / linear terms /
-// control quaternions of the spline window.
+// control quaternions of the spline window. One forward sweep of the spline (cached) + one reverse.
 __global__ void __launch_bounds__(128) rotation_backward_kernel(const __grid_constant__ FusedBwdArgs a)
 {
     const adgs_model& m = a.m;
@@ -455,9 +455,37 @@ __global__ void __launch_bounds__(128) rotation_backward_kernel(const __grid_con
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m.N_obj) return;
     const int g = m.N_scene + j;
-    Quat qt[ADGS_MAX_QUAT_ORDER + 1];
+    const float4* rd = reinterpret_cast<const float4*>(m.rot_deform);
+    float4 qraw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tb.quat.n_ctrl == 0) qraw = reinterpret_cast<const float4*>(m.rotation)[g];
+    for (int t = 0; t < tb.rotation.n; ++t) {
+        const float4 p = __ldg(rd + (size_t)tb.rotation.col[t] * m.N_obj + j);
+        const float w = tb.rotation.w0[t];
+        qraw.x += p.x * w;
+        qraw.y += p.y * w;
+        qraw.z += p.z * w;
+        qraw.w += p.w * w;
+    }
+    Quat qt[ADGS_MAX_QUAT_ORDER + 1], P[ADGS_MAX_QUAT_ORDER + 1];
+    float3 om[ADGS_MAX_QUAT_ORDER + 1];
     float norms[ADGS_MAX_QUAT_ORDER + 1];
-    const float4 qraw = object_rotation_raw(m, tb, g, j, qt, norms);
+    const int k = tb.quat.k;
+    if (tb.quat.n_ctrl != 0) {
+#pragma unroll
+        for (int i = 0; i <= ADGS_MAX_QUAT_ORDER; ++i) {
+            norms[i] = 1.f;
+            if (i <= k) {
+                qt[i] = ctrl_quat(__ldg(rd + (size_t)(tb.quat.start + i) * m.N_obj + j), norms[i]);
+            } else {
+                qt[i] = Quat{0.f, 0.f, 0.f, 1.f};
+            }
+        }
+        const Quat r = quat_spline_fwd_bwd(qt, k, tb.quat.cum, P, om);
+        qraw.x += r.w;
+        qraw.y += r.x;
+        qraw.z += r.y;
+        qraw.w += r.z;
+    }
     const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
     const float4 qhat = make_float4(qraw.x / qn, qraw.y / qn, qraw.z / qn, qraw.w / qn);
     const float4 graw = normalize4_bwd(qhat, qn, a.dq_scratch[j]);  // wxyz
@@ -469,9 +497,8 @@ __global__ void __launch_bounds__(128) rotation_backward_kernel(const __grid_con
         grd[(size_t)tb.rotation.col[t] * m.N_obj + j] = make_float4(graw.x * w, graw.y * w, graw.z * w, graw.w * w);
     }
     if (tb.quat.n_ctrl != 0) {
-        const int k = tb.quat.k;
         Quat gqt[ADGS_MAX_QUAT_ORDER + 1];
-        quat_spline_bwd(qt, k, tb.quat.cum, Quat{graw.y, graw.z, graw.w, graw.x}, gqt);
+        quat_spline_bwd(qt, k, tb.quat.cum, P, om, Quat{graw.y, graw.z, graw.w, graw.x}, gqt);
 #pragma unroll
         for (int i = 0; i <= ADGS_MAX_QUAT_ORDER; ++i) {
             if (i <= k) {

@@ -36,7 +36,7 @@ __device__ __forceinline__ Quat qadd(const Quat& a, const Quat& b)
 }
 
 // rotation vector of a unit quaternion, shortest arc
-__device__ __forceinline__ float3 qlog(Quat q)
+__device__ __noinline__ float3 qlog(Quat q)
 {
     if (q.w < 0.f) q = Quat{-q.x, -q.y, -q.z, -q.w};
     const float nv = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
@@ -52,7 +52,7 @@ __device__ __forceinline__ float3 qlog(Quat q)
 }
 
 // reverse mode of qlog: given g = dL/d(rotvec), returns dL/dq
-__device__ __forceinline__ Quat qlog_bwd(Quat q, const float3& g)
+__device__ __noinline__ Quat qlog_bwd(Quat q, const float3& g)
 {
     const float sgn = (q.w < 0.f) ? -1.f : 1.f;
     q = Quat{sgn * q.x, sgn * q.y, sgn * q.z, sgn * q.w};
@@ -83,7 +83,7 @@ __device__ __forceinline__ Quat qlog_bwd(Quat q, const float3& g)
     return r;
 }
 
-__device__ __forceinline__ Quat qexp(const float3& r)
+__device__ __noinline__ Quat qexp(const float3& r)
 {
     const float n = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z);
     float scale;
@@ -97,7 +97,7 @@ __device__ __forceinline__ Quat qexp(const float3& r)
 }
 
 // reverse mode of qexp: given g = dL/dq, returns dL/dr
-__device__ __forceinline__ float3 qexp_bwd(const float3& r, const Quat& g)
+__device__ __noinline__ float3 qexp_bwd(const float3& r, const Quat& g)
 {
     const float n2 = r.x * r.x + r.y * r.y + r.z * r.z;
     const float n = sqrtf(n2);
@@ -142,39 +142,44 @@ __device__ __forceinline__ Quat quat_spline(const Quat* qt, int k, const float* 
     return out;
 }
 
-// reverse mode of quat_spline: gqt[0..k] receive dL/dq_i (xyzw, w.r.t. the NORMALISED controls)
-__device__ __forceinline__ void quat_spline_bwd(const Quat* qt, int k, const float* cum, const Quat& gout, Quat* gqt)
+// reverse mode of quat_spline: gqt[0..k] receive dL/dq_i (xyzw, w.r.t. the NORMALISED controls).
+// One forward sweep caches the relative rotations, their logs and the prefix products; returns
+// the forward value q(t) so callers need not evaluate the spline separately.
+__device__ __forceinline__ Quat quat_spline_fwd_bwd(const Quat* qt, int k, const float* cum, Quat* P, float3* om)
 {
-    Quat P[ADGS_MAX_QUAT_ORDER + 1];
     P[0] = qt[0];
-#pragma unroll
-    for (int i = 0; i <= ADGS_MAX_QUAT_ORDER; ++i) gqt[i] = Quat{0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 1; i <= ADGS_MAX_QUAT_ORDER; ++i) {
         if (i <= k) {
-            const Quat rel = qmul(qconj(qt[i - 1]), qt[i]);
-            const float3 om = qlog(rel);
+            om[i] = qlog(qmul(qconj(qt[i - 1]), qt[i]));
             const float c = cum[i];
-            P[i] = qmul(P[i - 1], qexp(make_float3(c * om.x, c * om.y, c * om.z)));
+            P[i] = qmul(P[i - 1], qexp(make_float3(c * om[i].x, c * om[i].y, c * om[i].z)));
         } else {
             P[i] = P[i - 1];
+            om[i] = make_float3(0.f, 0.f, 0.f);
         }
     }
+    return P[ADGS_MAX_QUAT_ORDER];
+}
+
+__device__ __forceinline__ void quat_spline_bwd(const Quat* qt, int k, const float* cum, const Quat* P,
+                                                const float3* om, const Quat& gout, Quat* gqt)
+{
+#pragma unroll
+    for (int i = 0; i <= ADGS_MAX_QUAT_ORDER; ++i) gqt[i] = Quat{0.f, 0.f, 0.f, 0.f};
     Quat gP = gout;
 #pragma unroll
     for (int i = ADGS_MAX_QUAT_ORDER; i >= 1; --i) {
         if (i <= k) {
             const Quat a = qt[i - 1], b = qt[i];
-            const Quat rel = qmul(qconj(a), b);
-            const float3 om = qlog(rel);
             const float c = cum[i];
-            const float3 r = make_float3(c * om.x, c * om.y, c * om.z);
+            const float3 r = make_float3(c * om[i].x, c * om[i].y, c * om[i].z);
             const Quat e = qexp(r);
             const Quat ge = qmul(qconj(P[i - 1]), gP);
             gP = qmul(gP, qconj(e));
             const float3 gr = qexp_bwd(r, ge);
             const float3 gom = make_float3(c * gr.x, c * gr.y, c * gr.z);
-            const Quat grel = qlog_bwd(rel, gom);
+            const Quat grel = qlog_bwd(qmul(qconj(a), b), gom);
             const Quat gca = qmul(grel, qconj(b));
             gqt[i - 1] = qadd(gqt[i - 1], qconj(gca));
             gqt[i] = qadd(gqt[i], qmul(a, grel));
