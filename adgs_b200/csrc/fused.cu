@@ -672,8 +672,11 @@ int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const 
     carve(sc, grad_record, (size_t)N * ADGS_GRAD_FLOATS);
     carve(sc, dq_scratch, (size_t)(model->N_obj > 0 ? model->N_obj : 1));
     carve(sc, bg_scratch, 32);
-    cudaMemsetAsync(grad_record, 0, (size_t)N * ADGS_GRAD_FLOATS * sizeof(float), stream);
-    cudaMemsetAsync(bg_scratch, 0, 32 * sizeof(float), stream);
+    {
+        StageScope sc(kStageFills, stream);
+        cudaMemsetAsync(grad_record, 0, (size_t)N * ADGS_GRAD_FLOATS * sizeof(float), stream);
+        cudaMemsetAsync(bg_scratch, 0, 32 * sizeof(float), stream);
+    }
 
     const bool has_flow = basis->has_flow != 0;
     BlendBwdArgs b;
@@ -703,13 +706,42 @@ int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const 
         if ((st = check_stage("blend backward", debug, stream))) return st;
     }
 
-    // dense-gradient semantics: everything outside the active columns is zero
+    // dense-gradient semantics: everything outside the active columns is zero. The kernels write
+    // every active plane in full, so only the complement is memset (plane = all objects of a column).
     const int No = model->N_obj;
-    if (No > 0 && grads->xyz_deform && basis->xyz.n_cols > 0)
-        cudaMemsetAsync(grads->xyz_deform, 0, (size_t)basis->xyz.n_cols * 3 * No * sizeof(float), stream);
-    const int Cr = basis->rotation.n_cols;
-    if (No > 0 && grads->rot_deform && Cr > 0)
-        cudaMemsetAsync(grads->rot_deform, 0, (size_t)Cr * No * 4 * sizeof(float), stream);
+    {
+        StageScope sc(kStageFills, stream);
+        auto zero_inactive = [&](float* base, const adgs_lin_basis& lin, int quat_start, int quat_count,
+                                 size_t plane_floats) {
+            const int C = lin.n_cols;
+            if (!base || C <= 0 || No <= 0) return;
+            bool active[2 * ADGS_MAX_TERMS + 64];
+            const int cap = (int)(sizeof(active) / sizeof(active[0]));
+            if (C > cap) {
+                cudaMemsetAsync(base, 0, (size_t)C * plane_floats * sizeof(float), stream);
+                return;
+            }
+            for (int c = 0; c < C; ++c) active[c] = false;
+            for (int t = 0; t < lin.n; ++t) active[lin.col[t]] = true;
+            for (int i = 0; i < quat_count; ++i)
+                if (quat_start + i < C) active[quat_start + i] = true;
+            int c = 0;
+            while (c < C) {
+                if (active[c]) {
+                    ++c;
+                    continue;
+                }
+                int e = c;
+                while (e < C && !active[e]) ++e;
+                cudaMemsetAsync(base + (size_t)c * plane_floats, 0, (size_t)(e - c) * plane_floats * sizeof(float),
+                                stream);
+                c = e;
+            }
+        };
+        zero_inactive(grads->xyz_deform, basis->xyz, 0, 0, (size_t)3 * No);
+        zero_inactive(grads->rot_deform, basis->rotation, basis->quat.start,
+                      basis->quat.n_ctrl ? basis->quat.k + 1 : 0, (size_t)4 * No);
+    }
 
     FusedBwdArgs a;
     memset(&a, 0, sizeof(a));

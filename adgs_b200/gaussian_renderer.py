@@ -115,7 +115,10 @@ class _FusedRender(torch.autograd.Function):
         radii, geom, binning, img, saved, img_opacity = saved_t[len(PARAM_NAMES):]
         dev = tensors["xyz"].device
         N = model.get_pts_num
-        grads = {k: torch.empty_like(v) for k, v in tensors.items()}
+        # Gradient storage: fresh tensors, or -- when a multi-GPU step installed a sink -- fresh views of
+        # its flat all-reduce bucket, so that autograd adopts them without a copy (parallel.py).
+        sink = getattr(model, "_grad_sink", None)
+        grads = sink() if sink is not None else {k: torch.empty_like(v) for k, v in tensors.items()}
         d_means2D = torch.empty((N, 3), dtype=torch.float32, device=dev)
         overflow = False
         if ctx.pending is not None:

@@ -107,16 +107,21 @@ class MultiViewStep:
         for view in local:
             for p in params.values():
                 p.grad = None
-            res = render_fn(view)
-            outs, cots = cotangent_fn(view, res)
-            torch.autograd.backward(outs, cots)
+            # first local view: the backward writes straight into the flat bucket (no copy)
+            self.model._grad_sink = self.bucket.views if first else None
+            try:
+                res = render_fn(view)
+                outs, cots = cotangent_fn(view, res)
+                torch.autograd.backward(outs, cots)
+            finally:
+                self.model._grad_sink = None
             grads = {k: p.grad for k, p in params.items()}
+            v = self.bucket.views()
             if first:
-                v = self.bucket.views()
                 for k, g in grads.items():
                     if g is None:
                         v[k].zero_()
-                    else:
+                    elif g.data_ptr() != v[k].data_ptr():   # autograd cloned it (should not happen)
                         v[k].copy_(g)
                 first = False
             else:

@@ -285,20 +285,31 @@ def run_ours(args):
     h2d = sum(v.numel() * 4 for v in host_cot.values()) + sum(v.numel() * 4 for v in host_cam.values())
     d2h = 4
 
+    copy_stream = torch.cuda.Stream(device=device)
+
     def e2e_step():
-        c = {k: v.to(device, non_blocking=True) for k, v in host_cot.items()}
+        # host -> device: camera matrices first (needed by the forward), cotangent planes on a copy
+        # stream so that the PCIe transfer overlaps the forward; the backward waits for them.
         vc = cam._replace(**{k: v.to(device, non_blocking=True) for k, v in host_cam.items()})
+        copy_stream.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(copy_stream):
+            c = {k: v.to(device, non_blocking=True) for k, v in host_cot.items()}
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
         for p in params:
             p.grad = None
-        res = render(vc, model, None, pipe, flow_pkg=flow_pkg, render_objmask=True)
-        outs, cots = outputs_and_cotangents(res, c)
-        torch.autograd.backward(outs, cots)
+        model._grad_sink = mv.bucket.views if mv is not None else None
+        try:
+            res = render(vc, model, None, pipe, flow_pkg=flow_pkg, render_objmask=True)
+            torch.cuda.current_stream(device).wait_event(ready)
+            for v in c.values():
+                v.record_stream(torch.cuda.current_stream(device))
+            outs, cots = outputs_and_cotangents(res, c)
+            torch.autograd.backward(outs, cots)
+        finally:
+            model._grad_sink = None
         if mv is not None:
-            bucket = mv.bucket
-            v = bucket.views()
-            for k, p in zip(mv.names, params):
-                v[k].copy_(p.grad)
-            bucket.all_reduce()
+            mv.bucket.all_reduce()
         return float(res["img_opacity"].mean().item())   # device -> host read of a metric
 
     for _ in range(3):

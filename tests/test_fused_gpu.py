@@ -136,3 +136,40 @@ def test_trajectory_only_matches_oracle():
             got = model.get_deformed_pkg(t)
             for k in ("xyz", "rotation", "shs", "opacity"):
                 assert Hh.rel_err(got[k], want[k]) <= 1e-5, (key, t, k)
+
+
+def test_multi_view_step_sums_view_gradients():
+    """adgs_b200.parallel.MultiViewStep at world size 1: the flat bucket holds the SUM over views of
+    the single-view gradients (the multi-GPU oracle of SURVEY.md section 8e), the first view's
+    gradients being written straight into the bucket."""
+    from adgs_b200.parallel import MultiViewStep
+    order_args, ref, c = _scene(3000, 1000, "kitti75")
+    model = GaussianModel.from_reference({f: getattr(ref, f) for f in ref.FIELDS}, order_args)
+    cam = c["cam"]
+    cot = Hh.cotangents(c)
+    pipe = SimpleNamespace(inv_depth=True, debug=False, sync_free=True)
+
+    def vcam(t):
+        return SimpleNamespace(image_height=c["H"], image_width=c["W"], FoVx=cam.FoVx, FoVy=cam.FoVy,
+                               world_view_transform=cam.world_view_transform,
+                               full_proj_transform=cam.full_proj_transform, camera_center=cam.camera_center, time=t)
+
+    views = [(vcam(0.2), 0.25), (vcam(0.5), 0.55), (vcam(0.8), 0.75)]
+    render_fn = lambda v: render(v[0], model, None, pipe, flow_pkg=[v[1], None, None, None, None, None],
+                                 render_objmask=True)
+    cot_fn = lambda v, r: ((r["render"], r["depth"], r["img_flow"]), (cot["color"], cot["depth"][0], cot["flow"]))
+    want = None
+    for v in views:
+        model.zero_grad()
+        res = render_fn(v)
+        outs, cots = cot_fn(v, res)
+        torch.autograd.backward(outs, cots)
+        g = {k: getattr(model, k).grad.clone() for k in ("xyz", "sh4", "xyz_deform", "rot_deform", "gs_time_sigma",
+                                                          "background_deform")}
+        want = g if want is None else {k: want[k] + g[k] for k in g}
+    mv = MultiViewStep(model)
+    got = mv.run(views, render_fn, cot_fn)
+    for k in want:
+        assert Hh.rel_err(got[k], want[k]) <= 1e-5, k
+        assert getattr(model, k).grad.data_ptr() == got[k].data_ptr()
+    assert mv.stats.visible_count.max().item() <= 3 and mv.stats.visible_count.sum().item() > 0
