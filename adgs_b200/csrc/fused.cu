@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(128) rotation_backward_kernel(const __grid_con
         qraw.z += p.z * w;
         qraw.w += p.w * w;
     }
-    Quat qt[ADGS_MAX_QUAT_ORDER + 1], P[ADGS_MAX_QUAT_ORDER + 1];
+    Quat qt[ADGS_MAX_QUAT_ORDER + 1], P[ADGS_MAX_QUAT_ORDER + 1], E[ADGS_MAX_QUAT_ORDER + 1];
     float3 om[ADGS_MAX_QUAT_ORDER + 1];
     float norms[ADGS_MAX_QUAT_ORDER + 1];
     const int k = tb.quat.k;
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(128) rotation_backward_kernel(const __grid_con
                 qt[i] = Quat{0.f, 0.f, 0.f, 1.f};
             }
         }
-        const Quat r = quat_spline_fwd_bwd(qt, k, tb.quat.cum, P, om);
+        const Quat r = quat_spline_cached(qt, k, tb.quat.cum, P, E, om);
         qraw.x += r.w;
         qraw.y += r.x;
         qraw.z += r.y;
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(128) rotation_backward_kernel(const __grid_con
     }
     if (tb.quat.n_ctrl != 0) {
         Quat gqt[ADGS_MAX_QUAT_ORDER + 1];
-        quat_spline_bwd(qt, k, tb.quat.cum, P, om, Quat{graw.y, graw.z, graw.w, graw.x}, gqt);
+        quat_spline_bwd(qt, k, tb.quat.cum, P, E, om, Quat{graw.y, graw.z, graw.w, graw.x}, gqt);
 #pragma unroll
         for (int i = 0; i <= ADGS_MAX_QUAT_ORDER; ++i) {
             if (i <= k) {

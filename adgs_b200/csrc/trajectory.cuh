@@ -35,18 +35,20 @@ __device__ __forceinline__ Quat qadd(const Quat& a, const Quat& b)
     return Quat{a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
 }
 
-// rotation vector of a unit quaternion, shortest arc
+// rotation vector of a unit quaternion, shortest arc.  sin(angle/2) is taken from the quaternion
+// itself (sin(atan2(|v|, w)) = |v| / |q|), which is the same quantity roma evaluates with sinf.
 __device__ __noinline__ float3 qlog(Quat q)
 {
     if (q.w < 0.f) q = Quat{-q.x, -q.y, -q.z, -q.w};
-    const float nv = sqrtf(q.x * q.x + q.y * q.y + q.z * q.z);
+    const float nv2 = q.x * q.x + q.y * q.y + q.z * q.z;
+    const float nv = sqrtf(nv2);
     const float angle = 2.f * atan2f(nv, q.w);
     float scale;
     if (fabsf(angle) <= 1e-3f) {
         const float a2 = angle * angle;
         scale = 2.f + a2 / 12.f + 7.f * a2 * a2 / 2880.f;
     } else {
-        scale = angle / sinf(angle * 0.5f);
+        scale = angle * sqrtf(nv2 + q.w * q.w) / nv;
     }
     return make_float3(scale * q.x, scale * q.y, scale * q.z);
 }
@@ -58,6 +60,7 @@ __device__ __noinline__ Quat qlog_bwd(Quat q, const float3& g)
     q = Quat{sgn * q.x, sgn * q.y, sgn * q.z, sgn * q.w};
     const float nv2 = q.x * q.x + q.y * q.y + q.z * q.z;
     const float nv = sqrtf(nv2);
+    const float den = nv2 + q.w * q.w;
     const float angle = 2.f * atan2f(nv, q.w);
     float scale, dscale;  // scale(angle), d scale / d angle
     if (fabsf(angle) <= 1e-3f) {
@@ -65,13 +68,13 @@ __device__ __noinline__ Quat qlog_bwd(Quat q, const float3& g)
         scale = 2.f + a2 / 12.f + 7.f * a2 * a2 / 2880.f;
         dscale = angle / 6.f + 7.f * a2 * angle / 720.f;
     } else {
-        const float sh = sinf(angle * 0.5f), ch = cosf(angle * 0.5f);
+        const float inv_rho = rsqrtf(den);
+        const float sh = nv * inv_rho, ch = q.w * inv_rho;  // sin, cos of angle/2
         scale = angle / sh;
         dscale = (sh - 0.5f * angle * ch) / (sh * sh);
     }
     const float g_scale = g.x * q.x + g.y * q.y + g.z * q.z;
     const float g_half = 2.f * g_scale * dscale;  // d/d(half angle)
-    const float den = nv2 + q.w * q.w;
     const float g_nv = g_half * q.w / den;
     const float g_w = -g_half * nv / den;
     const float inv_nv = nv > 0.f ? 1.f / nv : 0.f;
@@ -86,18 +89,21 @@ __device__ __noinline__ Quat qlog_bwd(Quat q, const float3& g)
 __device__ __noinline__ Quat qexp(const float3& r)
 {
     const float n = sqrtf(r.x * r.x + r.y * r.y + r.z * r.z);
+    float sh, ch;
+    sincosf(n * 0.5f, &sh, &ch);
     float scale;
     if (n <= 1e-3f) {
         const float n2 = n * n;
         scale = 0.5f - n2 / 48.f + n2 * n2 / 3840.f;
     } else {
-        scale = sinf(n * 0.5f) / n;
+        scale = sh / n;
     }
-    return Quat{scale * r.x, scale * r.y, scale * r.z, cosf(n * 0.5f)};
+    return Quat{scale * r.x, scale * r.y, scale * r.z, ch};
 }
 
-// reverse mode of qexp: given g = dL/dq, returns dL/dr
-__device__ __noinline__ float3 qexp_bwd(const float3& r, const Quat& g)
+// reverse mode of qexp: given g = dL/dq and the forward value e = qexp(r), returns dL/dr.
+// cos(n/2) = e.w and sin(n/2) = |e.xyz| come from the forward value: no trigonometry here.
+__device__ __noinline__ float3 qexp_bwd(const float3& r, const Quat& e, const Quat& g)
 {
     const float n2 = r.x * r.x + r.y * r.y + r.z * r.z;
     const float n = sqrtf(n2);
@@ -105,11 +111,10 @@ __device__ __noinline__ float3 qexp_bwd(const float3& r, const Quat& g)
     if (n <= 1e-3f) {
         scale = 0.5f - n2 / 48.f + n2 * n2 / 3840.f;
         dscale_over_n = -1.f / 24.f + n2 / 960.f;
-        half_sin_over_n = n > 0.f ? 0.5f * sinf(n * 0.5f) / n : 0.f;
+        half_sin_over_n = 0.5f * scale;
     } else {
-        const float sh = sinf(n * 0.5f), ch = cosf(n * 0.5f);
-        scale = sh / n;
-        dscale_over_n = (0.5f * ch - scale) / n2;
+        scale = sqrtf(e.x * e.x + e.y * e.y + e.z * e.z) / n;
+        dscale_over_n = (0.5f * e.w - scale) / n2;
         half_sin_over_n = 0.5f * scale;
     }
     const float gv_dot_r = g.x * r.x + g.y * r.y + g.z * r.z;
@@ -142,10 +147,10 @@ __device__ __forceinline__ Quat quat_spline(const Quat* qt, int k, const float* 
     return out;
 }
 
-// reverse mode of quat_spline: gqt[0..k] receive dL/dq_i (xyzw, w.r.t. the NORMALISED controls).
-// One forward sweep caches the relative rotations, their logs and the prefix products; returns
-// the forward value q(t) so callers need not evaluate the spline separately.
-__device__ __forceinline__ Quat quat_spline_fwd_bwd(const Quat* qt, int k, const float* cum, Quat* P, float3* om)
+// Forward sweep that caches what the reverse sweep needs (log of every relative rotation, every
+// exponential, the prefix products); returns q(t).
+__device__ __forceinline__ Quat quat_spline_cached(const Quat* qt, int k, const float* cum, Quat* P, Quat* E,
+                                                   float3* om)
 {
     P[0] = qt[0];
 #pragma unroll
@@ -153,16 +158,19 @@ __device__ __forceinline__ Quat quat_spline_fwd_bwd(const Quat* qt, int k, const
         if (i <= k) {
             om[i] = qlog(qmul(qconj(qt[i - 1]), qt[i]));
             const float c = cum[i];
-            P[i] = qmul(P[i - 1], qexp(make_float3(c * om[i].x, c * om[i].y, c * om[i].z)));
+            E[i] = qexp(make_float3(c * om[i].x, c * om[i].y, c * om[i].z));
+            P[i] = qmul(P[i - 1], E[i]);
         } else {
             P[i] = P[i - 1];
+            E[i] = Quat{0.f, 0.f, 0.f, 1.f};
             om[i] = make_float3(0.f, 0.f, 0.f);
         }
     }
     return P[ADGS_MAX_QUAT_ORDER];
 }
 
-__device__ __forceinline__ void quat_spline_bwd(const Quat* qt, int k, const float* cum, const Quat* P,
+// reverse mode of quat_spline: gqt[0..k] receive dL/dq_i (xyzw, w.r.t. the NORMALISED controls)
+__device__ __forceinline__ void quat_spline_bwd(const Quat* qt, int k, const float* cum, const Quat* P, const Quat* E,
                                                 const float3* om, const Quat& gout, Quat* gqt)
 {
 #pragma unroll
@@ -174,10 +182,9 @@ __device__ __forceinline__ void quat_spline_bwd(const Quat* qt, int k, const flo
             const Quat a = qt[i - 1], b = qt[i];
             const float c = cum[i];
             const float3 r = make_float3(c * om[i].x, c * om[i].y, c * om[i].z);
-            const Quat e = qexp(r);
             const Quat ge = qmul(qconj(P[i - 1]), gP);
-            gP = qmul(gP, qconj(e));
-            const float3 gr = qexp_bwd(r, ge);
+            gP = qmul(gP, qconj(E[i]));
+            const float3 gr = qexp_bwd(r, E[i], ge);
             const float3 gom = make_float3(c * gr.x, c * gr.y, c * gr.z);
             const Quat grel = qlog_bwd(qmul(qconj(a), b), gom);
             const Quat gca = qmul(grel, qconj(b));

@@ -298,7 +298,25 @@ class GaussianModel(nn.Module):
         self._binning_capacity = max(self._binning_capacity, int(1.3 * R) + 65536)
 
     def time_basis(self, t, flow_t=None) -> L.TimeBasis:
-        return make_time_basis(self.order_args, t, flow_t, self.use_time_mask)
+        """Host-side basis for (t, flow_t); cached -- a training run revisits the same frame times."""
+        key = (float(t), None if flow_t is None else float(flow_t), bool(self.use_time_mask))
+        cache = self.__dict__.setdefault("_basis_cache", {})
+        tb = cache.get(key)
+        if tb is None:
+            if len(cache) > 4096:
+                cache.clear()
+            tb = make_time_basis(self.order_args, t, flow_t, self.use_time_mask)
+            cache[key] = tb
+        return tb
+
+    def _pinned_counters(self):
+        """Small ring of pinned int32[2] buffers for the asynchronous {num_rendered, overflow} read-back."""
+        ring = self.__dict__.setdefault("_counter_ring", [])
+        if len(ring) < 8:
+            ring.append(torch.empty((2,), dtype=torch.int32).pin_memory())
+            return ring[-1]
+        self.__dict__["_counter_idx"] = (self.__dict__.get("_counter_idx", -1) + 1) % len(ring)
+        return ring[self.__dict__["_counter_idx"]]
 
     # ---- trajectory alone (drop-in for get_deformed_* ; values only, see gaussian_renderer.render for grads)
     @torch.no_grad()

@@ -78,7 +78,7 @@ class _FusedRender(torch.autograd.Function):
                                              C.byref(images), C.byref(dfm), L.ptr(geom), L.ptr(binning), capacity,
                                              _NULL_CB, None, L.ptr(img), L.ptr(saved), stream)
                 L.check(st, "render_forward")
-                counters = torch.empty((2,), dtype=torch.int32).pin_memory()
+                counters = model._pinned_counters()
                 L.check(lib.adgs_read_counters(L.ptr(geom), N, counters.data_ptr(), stream), "read_counters")
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream(dev))
@@ -155,11 +155,10 @@ class _FusedRender(torch.autograd.Function):
 def render(viewpoint_camera, pc: GaussianModel, env_map, pipe, scaling_modifier=1.0, override_color=None,
            flow_pkg=None, render_objmask=False):
     """Render the scene (same contract as gaussian_renderer/__init__.py:18-115)."""
-    screenspace_points = torch.zeros_like(pc.get_xyz, dtype=pc.get_xyz.dtype, requires_grad=True, device=pc.xyz.device) + 0
-    try:
-        screenspace_points.retain_grad()
-    except Exception:
-        pass
+    # zero tensor whose .grad receives the screen-space mean gradients (gaussian_renderer/__init__.py:26-30);
+    # a leaf, so no retain_grad() and no extra "+ 0" kernel is needed
+    screenspace_points = torch.zeros((pc.get_pts_num, 3), dtype=torch.float32, device=pc.xyz.device,
+                                     requires_grad=True)
 
     dev = pc.xyz.device
     tanfovx = math.tan(viewpoint_camera.FoVx * 0.5)

@@ -279,31 +279,45 @@ def run_ours(args):
                      "frac_of_hbm_peak": round(step_ach / peak, 4), "num_rendered": R}
 
     # ---- e2e: host buffers in, host metric out, every step ---------------------------------------------
-    host_cot = make_cotangents(wl, device, pinned=True)
-    host_cam = {k: getattr(cam, k).cpu().pin_memory() for k in ("world_view_transform", "full_proj_transform",
-                                                                "camera_center")}
-    h2d = sum(v.numel() * 4 for v in host_cot.values()) + sum(v.numel() * 4 for v in host_cam.values())
+    # host-side inputs of one step, each group packed in ONE pinned buffer (one H2D copy per group):
+    # the five cotangent planes (standing in for the ground-truth images the losses consume) and
+    # the camera (view matrix, full projection, centre).
+    H, W = wl["H"], wl["W"]
+    hc = make_cotangents(wl, device, pinned=False)
+    host_cot = torch.cat([hc[k].cpu().reshape(-1) for k in ("color", "depth", "opacity", "flow", "semantic")]).pin_memory()
+    host_cam = torch.cat([cam.world_view_transform.cpu().reshape(-1), cam.full_proj_transform.cpu().reshape(-1),
+                          cam.camera_center.cpu().reshape(-1)]).pin_memory()
+    h2d = host_cot.numel() * 4 + host_cam.numel() * 4
     d2h = 4
+
+    def split_cot(flat):
+        px_ = H * W
+        o, out = 0, {}
+        for k, ch in (("color", 3), ("depth", 1), ("opacity", 1), ("flow", 3), ("semantic", 1)):
+            out[k] = flat[o:o + ch * px_].view(ch, H, W)
+            o += ch * px_
+        return out
 
     copy_stream = torch.cuda.Stream(device=device)
 
     def e2e_step():
         # host -> device: camera matrices first (needed by the forward), cotangent planes on a copy
         # stream so that the PCIe transfer overlaps the forward; the backward waits for them.
-        vc = cam._replace(**{k: v.to(device, non_blocking=True) for k, v in host_cam.items()})
-        copy_stream.wait_stream(torch.cuda.current_stream(device))
+        dcam = host_cam.to(device, non_blocking=True)
+        vc = cam._replace(world_view_transform=dcam[0:16].view(4, 4), full_proj_transform=dcam[16:32].view(4, 4),
+                          camera_center=dcam[32:35])
         with torch.cuda.stream(copy_stream):
-            c = {k: v.to(device, non_blocking=True) for k, v in host_cot.items()}
+            flat = host_cot.to(device, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(copy_stream)
+        c = split_cot(flat)
         for p in params:
             p.grad = None
         model._grad_sink = mv.bucket.views if mv is not None else None
         try:
             res = render(vc, model, None, pipe, flow_pkg=flow_pkg, render_objmask=True)
             torch.cuda.current_stream(device).wait_event(ready)
-            for v in c.values():
-                v.record_stream(torch.cuda.current_stream(device))
+            flat.record_stream(torch.cuda.current_stream(device))
             outs, cots = outputs_and_cotangents(res, c)
             torch.autograd.backward(outs, cots)
         finally:
