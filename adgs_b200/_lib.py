@@ -177,6 +177,17 @@ class Deformed(C.Structure):
     ]
 
 
+class Splats(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32),
+        ("_pad", C.c_int32),
+        ("record", C.c_void_p),
+        ("depth_keys", C.c_void_p),
+        ("tiles_touched", C.c_void_p),
+        ("radii", C.c_void_p),
+    ]
+
+
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 
 _P = C.POINTER
@@ -215,6 +226,15 @@ SIGNATURES = {
     "adgs_render_backward": (C.c_int, [_P(Camera), _P(Model), _P(TimeBasis), C.c_int32, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, _P(ImageGrads),
                                        _P(Model), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adgs_shard_state_bytes": (C.c_size_t, [C.c_int32]),
+    "adgs_shard_forward": (C.c_int, [_P(Camera), _P(Model), _P(TimeBasis), C.c_int32, _P(Splats), C.c_void_p,
+                                     C.c_void_p]),
+    "adgs_splats_forward": (C.c_int, [_P(Camera), _P(Splats), C.c_int32, C.c_int32, _P(Images), C.c_void_p, C.c_void_p,
+                                      C.c_int64, ALLOC_FN, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adgs_splats_backward": (C.c_int, [_P(Camera), _P(Splats), C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
+                                       C.c_void_p, _P(ImageGrads), C.c_void_p, C.c_void_p]),
+    "adgs_shard_backward": (C.c_int, [_P(Camera), _P(Model), _P(TimeBasis), C.c_void_p, C.c_void_p, C.c_void_p,
+                                      _P(Model), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "adgs_launch_count": (C.c_ulonglong, []),
     "adgs_profile_begin": (C.c_int, []),
     "adgs_profile_num_stages": (C.c_int, []),

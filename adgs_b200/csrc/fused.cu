@@ -280,7 +280,35 @@ struct FusedBwdArgs {
     float* dL_dmeans2D;
     float4* dq_scratch;  // (N_obj) dL/d(normalised object quaternion)
     float* bg_scratch;   // 6 floats: sum dxyz_t, sum dflow
+    int accumulate;      // != 0: add into the gradient buffers (second and later views of a batch)
 };
+
+__device__ __forceinline__ void put(float* p, float v, int acc)
+{
+    *p = acc ? *p + v : v;
+}
+
+__device__ __forceinline__ void put2(float2* p, float2 v, int acc)
+{
+    if (acc) {
+        const float2 o = *p;
+        v.x += o.x;
+        v.y += o.y;
+    }
+    *p = v;
+}
+
+__device__ __forceinline__ void put4(float4* p, float4 v, int acc)
+{
+    if (acc) {
+        const float4 o = *p;
+        v.x += o.x;
+        v.y += o.y;
+        v.z += o.z;
+        v.w += o.w;
+    }
+    *p = v;
+}
 
 __global__ void __launch_bounds__(256, 2) fused_backward_kernel(const __grid_constant__ FusedBwdArgs a)
 {
@@ -364,13 +392,14 @@ __global__ void __launch_bounds__(256, 2) fused_backward_kernel(const __grid_con
         // ---- leaf gradients ----------------------------------------------------------------
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
-            a.g.xyz[3 * (size_t)g + d] = dxt[d] + dfl[d];
-            a.g.scaling[3 * (size_t)g + d] = dscale[d] * scale[d];
+            put(a.g.xyz + 3 * (size_t)g + d, dxt[d] + dfl[d], a.accumulate);
+            put(a.g.scaling + 3 * (size_t)g + d, dscale[d] * scale[d], a.accumulate);
         }
         float4* gsh4 = reinterpret_cast<float4*>(a.g.sh4);
 #pragma unroll
         for (int q = 0; q < 12; ++q)
-            gsh4[(size_t)q * N + g] = make_float4(dsh[4 * q], dsh[4 * q + 1], dsh[4 * q + 2], dsh[4 * q + 3]);
+            put4(gsh4 + (size_t)q * N + g, make_float4(dsh[4 * q], dsh[4 * q + 1], dsh[4 * q + 2], dsh[4 * q + 3]),
+                 a.accumulate);
         if (a.g.shs_deform4 && Cs > 0) {
             const int nq = (3 * Cs + 3) / 4;
             float4* gsd = reinterpret_cast<float4*>(a.g.shs_deform4);
@@ -382,7 +411,7 @@ __global__ void __launch_bounds__(256, 2) fused_backward_kernel(const __grid_con
                     const int c = e / Cs;
                     v[e4] = (c < 3) ? dsh[c] * s_wshs[e - c * Cs] : 0.f;
                 }
-                gsd[(size_t)q * N + g] = make_float4(v[0], v[1], v[2], v[3]);
+                put4(gsd + (size_t)q * N + g, make_float4(v[0], v[1], v[2], v[3]), a.accumulate);
             }
         }
         // opacity: op_act = sigmoid(o) [* mask]
@@ -399,18 +428,20 @@ __global__ void __launch_bounds__(256, 2) fused_backward_kernel(const __grid_con
                 mask = expf(-0.5f * z * z);
                 const float dside = dop * sig * mask * z * z;
                 if (a.g.gs_time_sigma)
-                    reinterpret_cast<float2*>(a.g.gs_time_sigma)[j] = neg ? make_float2(dside, 0.f) : make_float2(0.f, dside);
+                    put2(reinterpret_cast<float2*>(a.g.gs_time_sigma) + j,
+                         neg ? make_float2(dside, 0.f) : make_float2(0.f, dside), a.accumulate);
             } else if (is_obj && a.g.gs_time_sigma) {
-                reinterpret_cast<float2*>(a.g.gs_time_sigma)[j] = make_float2(0.f, 0.f);
+                put2(reinterpret_cast<float2*>(a.g.gs_time_sigma) + j, make_float2(0.f, 0.f), a.accumulate);
             }
-            a.g.opacity[g] = dop * mask * sig * (1.f - sig);
+            put(a.g.opacity + g, dop * mask * sig * (1.f - sig), a.accumulate);
         }
         // rotation
         if (!is_obj) {
             const float4 qraw = reinterpret_cast<const float4*>(m.rotation)[g];
             const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
-            reinterpret_cast<float4*>(a.g.rotation)[g] =
-                normalize4_bwd(make_float4(rot[0], rot[1], rot[2], rot[3]), qn, make_float4(dq[0], dq[1], dq[2], dq[3]));
+            put4(reinterpret_cast<float4*>(a.g.rotation) + g,
+                 normalize4_bwd(make_float4(rot[0], rot[1], rot[2], rot[3]), qn, make_float4(dq[0], dq[1], dq[2], dq[3])),
+                 a.accumulate);
         } else {
             a.dq_scratch[j] = make_float4(dq[0], dq[1], dq[2], dq[3]);
         }
@@ -420,7 +451,7 @@ __global__ void __launch_bounds__(256, 2) fused_backward_kernel(const __grid_con
                 float* o = a.g.xyz_deform + ((size_t)tb.xyz.col[t] * 3) * m.N_obj + j;
                 const float w0 = tb.xyz.w0[t], w1 = tb.xyz.w1[t];
 #pragma unroll
-                for (int d = 0; d < 3; ++d) o[(size_t)d * m.N_obj] = dxt[d] * w0 + dfl[d] * w1;
+                for (int d = 0; d < 3; ++d) put(o + (size_t)d * m.N_obj, dxt[d] * w0 + dfl[d] * w1, a.accumulate);
             }
         }
     }
@@ -489,12 +520,14 @@ __global__ void __launch_bounds__(128) rotation_backward_kernel(const __grid_con
     const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
     const float4 qhat = make_float4(qraw.x / qn, qraw.y / qn, qraw.z / qn, qraw.w / qn);
     const float4 graw = normalize4_bwd(qhat, qn, a.dq_scratch[j]);  // wxyz
-    reinterpret_cast<float4*>(a.g.rotation)[g] = (tb.quat.n_ctrl == 0) ? graw : make_float4(0.f, 0.f, 0.f, 0.f);
+    put4(reinterpret_cast<float4*>(a.g.rotation) + g, (tb.quat.n_ctrl == 0) ? graw : make_float4(0.f, 0.f, 0.f, 0.f),
+         a.accumulate);
     float4* grd = reinterpret_cast<float4*>(a.g.rot_deform);
     if (!grd) return;
     for (int t = 0; t < tb.rotation.n; ++t) {
         const float w = tb.rotation.w0[t];
-        grd[(size_t)tb.rotation.col[t] * m.N_obj + j] = make_float4(graw.x * w, graw.y * w, graw.z * w, graw.w * w);
+        put4(grd + (size_t)tb.rotation.col[t] * m.N_obj + j, make_float4(graw.x * w, graw.y * w, graw.z * w, graw.w * w),
+             a.accumulate);
     }
     if (tb.quat.n_ctrl != 0) {
         Quat gqt[ADGS_MAX_QUAT_ORDER + 1];
@@ -505,7 +538,7 @@ __global__ void __launch_bounds__(128) rotation_backward_kernel(const __grid_con
                 // control = normalize(param + e_w): back through the normalisation, xyzw -> wxyz
                 const float4 nq = make_float4(qt[i].w, qt[i].x, qt[i].y, qt[i].z);
                 const float4 gg = make_float4(gqt[i].w, gqt[i].x, gqt[i].y, gqt[i].z);
-                grd[(size_t)(tb.quat.start + i) * m.N_obj + j] = normalize4_bwd(nq, norms[i], gg);
+                put4(grd + (size_t)(tb.quat.start + i) * m.N_obj + j, normalize4_bwd(nq, norms[i], gg), a.accumulate);
             }
         }
     }
@@ -517,7 +550,8 @@ __global__ void background_finalize_kernel(const __grid_constant__ FusedBwdArgs 
     float* out = a.g.background_deform;
     if (!out) return;
     const int C = b.n_cols;
-    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) out[i] = 0.f;
+    if (!a.accumulate)
+        for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) out[i] = 0.f;
     __syncthreads();
     if (threadIdx.x < 3) {
         const int d = threadIdx.x;
@@ -547,6 +581,168 @@ int validate_model(const adgs_model* m, const adgs_time_basis* tb)
     }
     if (tb->shs.n && !m->shs_deform4) return ADGS_ERR_ARG;
     if (tb->background.n && !m->background_deform) return ADGS_ERR_ARG;
+    return ADGS_OK;
+}
+
+
+// ---- host-side stages shared by the single-GPU entry points and the splat-exchange entry points ----
+
+struct SplatPtrs {  // per-Gaussian per-view state consumed by binning + blend
+    float4* record;
+    uint32_t* depth_keys;
+    uint32_t* tiles_touched;
+    int32_t* radii;
+};
+
+int run_per_gaussian_forward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
+                             int render_objmask, const adgs_deformed* deformed, const SplatPtrs& sp, float* cov3D,
+                             uint8_t* clamped, float4* saved, cudaStream_t stream)
+{
+    const int N = model->N_scene + model->N_obj;
+    FusedFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = *model;
+    a.tb = *basis;
+    if (deformed) a.out = *deformed;
+    a.render = 1;
+    a.render_objmask = render_objmask;
+    a.rp = make_raster_params(cam);
+    a.view = cam->viewmatrix;
+    a.proj = cam->projmatrix;
+    a.campos = cam->campos;
+    a.radii = sp.radii;
+    a.depth_keys = sp.depth_keys;
+    a.tiles_touched = sp.tiles_touched;
+    a.record = sp.record;
+    a.cov3D = cov3D;
+    a.clamped = clamped;
+    a.saved = saved;
+    {
+        StageScope sc(kStagePerGaussianFwd, stream);
+        fused_forward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+        count_launch(1);
+    }
+    return check_stage("fused forward", cam->debug != 0, stream);
+}
+
+int run_blend_backward(const adgs_camera* cam, int P, int render_objmask, bool has_flow, const float4* record,
+                       const BinningState& bs, const ImageState& is, int64_t capacity, const float* img_opacity,
+                       const adgs_image_grads* dpix, float* grad_record, cudaStream_t stream)
+{
+    const RasterParams rp = make_raster_params(cam);
+    {
+        StageScope sc(kStageFills, stream);
+        cudaMemsetAsync(grad_record, 0, (size_t)P * ADGS_GRAD_FLOATS * sizeof(float), stream);
+    }
+    BlendBwdArgs b;
+    b.ranges = is.ranges;
+    b.point_list = sorted_point_list(bs, rp.grid_x * rp.grid_y);
+    b.record = record;
+    b.semantic = nullptr;
+    b.bg = cam->bg;
+    b.W = rp.W;
+    b.H = rp.H;
+    b.D_S = render_objmask ? 1 : 0;
+    b.n_contrib = is.n_contrib;
+    b.img_opacity = img_opacity;
+    b.dL_dcolor = dpix->dL_dcolor;
+    b.dL_ddepth = dpix->dL_ddepth;
+    b.dL_dflow = has_flow ? dpix->dL_dflow : nullptr;
+    // the object mask itself is a constant, but its image cotangent still reaches alpha (backward.cu:597-603)
+    b.dL_dsemantic = render_objmask ? dpix->dL_dsemantic : nullptr;
+    b.dL_dopacity = dpix->dL_dopacity;
+    b.grad_record = grad_record;
+    b.dL_dsemantic_g = nullptr;
+    if (capacity > 0) {
+        StageScope sc(kStageBlendBwd, stream);
+        launch_blend_backward(b, has_flow, stream);
+    }
+    return check_stage("blend backward", cam->debug != 0, stream);
+}
+
+int run_per_gaussian_backward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
+                              const int32_t* radii, const float* cov3D, const uint8_t* clamped, const float4* saved,
+                              const float* grad_record, const adgs_model* grads, int accumulate, float* dL_dmeans2D,
+                              float4* dq_scratch, float* bg_scratch, cudaStream_t stream)
+{
+    const bool debug = cam->debug != 0;
+    const int N = model->N_scene + model->N_obj;
+    const int No = model->N_obj;
+    int st;
+    {
+        // dense-gradient semantics: everything outside the active columns is zero. The kernels write
+        // every active plane in full, so only the complement is memset (plane = all objects of a
+        // column); when accumulating over the views of a batch only the first view fills.
+        StageScope sc(kStageFills, stream);
+        cudaMemsetAsync(bg_scratch, 0, 32 * sizeof(float), stream);
+        auto zero_inactive = [&](float* base, const adgs_lin_basis& lin, int quat_start, int quat_count,
+                                 size_t plane_floats) {
+            const int C = lin.n_cols;
+            if (!base || C <= 0 || No <= 0) return;
+            bool active[2 * ADGS_MAX_TERMS + 64];
+            const int cap = (int)(sizeof(active) / sizeof(active[0]));
+            if (C > cap) {
+                cudaMemsetAsync(base, 0, (size_t)C * plane_floats * sizeof(float), stream);
+                return;
+            }
+            for (int c = 0; c < C; ++c) active[c] = false;
+            for (int t = 0; t < lin.n; ++t) active[lin.col[t]] = true;
+            for (int i = 0; i < quat_count; ++i)
+                if (quat_start + i < C) active[quat_start + i] = true;
+            int c = 0;
+            while (c < C) {
+                if (active[c]) {
+                    ++c;
+                    continue;
+                }
+                int e = c;
+                while (e < C && !active[e]) ++e;
+                cudaMemsetAsync(base + (size_t)c * plane_floats, 0, (size_t)(e - c) * plane_floats * sizeof(float),
+                                stream);
+                c = e;
+            }
+        };
+        if (!accumulate) {
+            zero_inactive(grads->xyz_deform, basis->xyz, 0, 0, (size_t)3 * No);
+            zero_inactive(grads->rot_deform, basis->rotation, basis->quat.start,
+                          basis->quat.n_ctrl ? basis->quat.k + 1 : 0, (size_t)4 * No);
+        }
+    }
+    FusedBwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = *model;
+    a.g = *grads;
+    a.tb = *basis;
+    a.rp = make_raster_params(cam);
+    a.view = cam->viewmatrix;
+    a.proj = cam->projmatrix;
+    a.campos = cam->campos;
+    a.radii = radii;
+    a.cov3D = cov3D;
+    a.clamped = clamped;
+    a.saved = saved;
+    a.grad_record = grad_record;
+    a.dL_dmeans2D = dL_dmeans2D;
+    a.dq_scratch = dq_scratch;
+    a.bg_scratch = bg_scratch;
+    a.accumulate = accumulate;
+    {
+        StageScope sc(kStagePerGaussianBwd, stream);
+        fused_backward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+        count_launch(1);
+    }
+    if ((st = check_stage("fused backward", debug, stream))) return st;
+    if (No > 0) {
+        StageScope sc(kStageRotationBwd, stream);
+        rotation_backward_kernel<<<(No + 127) / 128, 128, 0, stream>>>(a);
+        count_launch(1);
+    }
+    if ((st = check_stage("rotation backward", debug, stream))) return st;
+    if (grads->background_deform && basis->background.n_cols > 0) {
+        count_launch(1);
+        background_finalize_kernel<<<1, 128, 0, stream>>>(a);
+        if ((st = check_stage("background finalize", debug, stream))) return st;
+    }
     return ADGS_OK;
 }
 
@@ -582,6 +778,19 @@ size_t adgs_render_saved_bytes(int32_t N)
     return (size_t)(N > 0 ? N : 0) * kSavedFloats * sizeof(float) + 256;
 }
 
+size_t adgs_render_scratch_bytes(int32_t N, int32_t N_obj)
+{
+    return (size_t)(N > 0 ? N : 0) * ADGS_GRAD_FLOATS * sizeof(float) + (size_t)(N_obj > 0 ? N_obj : 1) * 16 + 1024;
+}
+
+static int check_render_args(const adgs_camera* cam)
+{
+    if (!cam || !cam->viewmatrix || !cam->projmatrix || !cam->campos || !cam->bg) return ADGS_ERR_ARG;
+    if (cam->image_width <= 0 || cam->image_height <= 0) return ADGS_ERR_ARG;
+    if (cam->sh_degree < 0 || cam->sh_degree > 3) return ADGS_ERR_UNSUPPORTED;
+    return ADGS_OK;
+}
+
 int adgs_render_forward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
                         int32_t render_objmask, const adgs_images* out, const adgs_deformed* deformed,
                         char* geometry, char* binning, int64_t capacity, adgs_alloc_fn binning_alloc,
@@ -590,53 +799,27 @@ int adgs_render_forward(const adgs_camera* cam, const adgs_model* model, const a
     cudaStream_t stream = (cudaStream_t)stream_;
     int st = validate_model(model, basis);
     if (st) return st;
-    if (!cam || !out || !geometry || !image || !saved || capacity < 0) return ADGS_ERR_ARG;
+    if ((st = check_render_args(cam))) return st;
+    if (!out || !geometry || !image || !saved || capacity < 0) return ADGS_ERR_ARG;
     if (!binning && !binning_alloc) return ADGS_ERR_ARG;
-    if (!out->depth || !out->opacity || !cam->viewmatrix || !cam->projmatrix || !cam->campos || !cam->bg)
-        return ADGS_ERR_ARG;
-    if (cam->sh_degree < 0 || cam->sh_degree > 3) return ADGS_ERR_UNSUPPORTED;
+    if (!out->depth || !out->opacity) return ADGS_ERR_ARG;
     const int N = model->N_scene + model->N_obj;
     if (N == 0) return ADGS_ERR_ARG;
     GeometryState gs = GeometryState::from_chunk(geometry, (size_t)N);
     ImageState is = ImageState::from_chunk(image, cam->image_width, cam->image_height);
     cudaMemsetAsync(gs.counters, 0, 32 * sizeof(uint32_t), stream);
     int32_t* radii = out->radii ? out->radii : gs.radii;
-
-    FusedFwdArgs a;
-    memset(&a, 0, sizeof(a));
-    a.m = *model;
-    a.tb = *basis;
-    if (deformed) a.out = *deformed;
-    a.render = 1;
-    a.render_objmask = render_objmask;
-    a.rp = make_raster_params(cam);
-    a.view = cam->viewmatrix;
-    a.proj = cam->projmatrix;
-    a.campos = cam->campos;
-    a.radii = radii;
-    a.depth_keys = gs.depth_keys;
-    a.tiles_touched = gs.tiles_touched;
-    a.record = reinterpret_cast<float4*>(gs.record);
-    a.cov3D = gs.cov3D;
-    a.clamped = gs.clamped;
     char* sc = saved;
-    carve(sc, a.saved, (size_t)N * 3);
-    {
-        StageScope sc(kStagePerGaussianFwd, stream);
-        fused_forward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
-        count_launch(1);
-    }
-    st = check_stage("fused forward", cam->debug != 0, stream);
-    if (st) return st;
+    float4* saved4 = nullptr;
+    carve(sc, saved4, (size_t)N * 3);
+    SplatPtrs sp{reinterpret_cast<float4*>(gs.record), gs.depth_keys, gs.tiles_touched, radii};
+    if ((st = run_per_gaussian_forward(cam, model, basis, render_objmask, deformed, sp, gs.cov3D, gs.clamped, saved4,
+                                       stream)))
+        return st;
     int R = 0;
     st = bin_and_blend(cam, N, render_objmask ? 1 : 0, basis->has_flow != 0, nullptr, out, radii, gs, binning,
                        binning_alloc, alloc_user, capacity, is, binning == nullptr, &R, stream);
     return st ? st : R;
-}
-
-size_t adgs_render_scratch_bytes(int32_t N, int32_t N_obj)
-{
-    return (size_t)(N > 0 ? N : 0) * ADGS_GRAD_FLOATS * sizeof(float) + (size_t)(N_obj > 0 ? N_obj : 1) * 16 + 1024;
 }
 
 int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
@@ -648,23 +831,20 @@ int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const 
     cudaStream_t stream = (cudaStream_t)stream_;
     int st = validate_model(model, basis);
     if (st) return st;
-    if (!cam || !geometry || !binning || !image || !saved || !img_opacity || !dpix || !grads || !scratch ||
-        capacity < 0)
+    if ((st = check_render_args(cam))) return st;
+    if (!geometry || !binning || !image || !saved || !img_opacity || !dpix || !grads || !scratch || capacity < 0)
         return ADGS_ERR_ARG;
     if (!grads->xyz || !grads->scaling || !grads->rotation || !grads->opacity || !grads->sh4) return ADGS_ERR_ARG;
     const int N = model->N_scene + model->N_obj;
     if (N == 0) return ADGS_ERR_ARG;
-    const bool debug = cam->debug != 0;
-    const RasterParams rp = make_raster_params(cam);
     char* gc = const_cast<char*>(geometry);
     char* bc = const_cast<char*>(binning);
     char* ic = const_cast<char*>(image);
     char* svc = const_cast<char*>(saved);
     GeometryState gs = GeometryState::from_chunk(gc, (size_t)N);
     BinningState bs = BinningState::from_chunk(bc, (size_t)capacity);
-    ImageState is = ImageState::from_chunk(ic, rp.W, rp.H);
+    ImageState is = ImageState::from_chunk(ic, cam->image_width, cam->image_height);
     if (!radii) radii = gs.radii;
-
     char* sc = scratch;
     float* grad_record = nullptr;
     float4* dq_scratch = nullptr;
@@ -672,115 +852,119 @@ int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const 
     carve(sc, grad_record, (size_t)N * ADGS_GRAD_FLOATS);
     carve(sc, dq_scratch, (size_t)(model->N_obj > 0 ? model->N_obj : 1));
     carve(sc, bg_scratch, 32);
-    {
-        StageScope sc(kStageFills, stream);
-        cudaMemsetAsync(grad_record, 0, (size_t)N * ADGS_GRAD_FLOATS * sizeof(float), stream);
-        cudaMemsetAsync(bg_scratch, 0, 32 * sizeof(float), stream);
-    }
-
-    const bool has_flow = basis->has_flow != 0;
-    BlendBwdArgs b;
-    b.ranges = is.ranges;
-    b.point_list = sorted_point_list(bs, rp.grid_x * rp.grid_y);
-    b.record = reinterpret_cast<const float4*>(gs.record);
-    b.semantic = nullptr;
-    b.bg = cam->bg;
-    b.W = rp.W;
-    b.H = rp.H;
-    b.D_S = render_objmask ? 1 : 0;
-    b.n_contrib = is.n_contrib;
-    b.img_opacity = img_opacity;
-    b.dL_dcolor = dpix->dL_dcolor;
-    b.dL_ddepth = dpix->dL_ddepth;
-    b.dL_dflow = has_flow ? dpix->dL_dflow : nullptr;
-    // the object mask itself is a constant, but its image cotangent still reaches alpha (backward.cu:597-603)
-    b.dL_dsemantic = render_objmask ? dpix->dL_dsemantic : nullptr;
-    b.dL_dopacity = dpix->dL_dopacity;
-    b.grad_record = grad_record;
-    b.dL_dsemantic_g = nullptr;
-    if (capacity > 0) {
-        {
-            StageScope sc(kStageBlendBwd, stream);
-            launch_blend_backward(b, has_flow, stream);
-        }
-        if ((st = check_stage("blend backward", debug, stream))) return st;
-    }
-
-    // dense-gradient semantics: everything outside the active columns is zero. The kernels write
-    // every active plane in full, so only the complement is memset (plane = all objects of a column).
-    const int No = model->N_obj;
-    {
-        StageScope sc(kStageFills, stream);
-        auto zero_inactive = [&](float* base, const adgs_lin_basis& lin, int quat_start, int quat_count,
-                                 size_t plane_floats) {
-            const int C = lin.n_cols;
-            if (!base || C <= 0 || No <= 0) return;
-            bool active[2 * ADGS_MAX_TERMS + 64];
-            const int cap = (int)(sizeof(active) / sizeof(active[0]));
-            if (C > cap) {
-                cudaMemsetAsync(base, 0, (size_t)C * plane_floats * sizeof(float), stream);
-                return;
-            }
-            for (int c = 0; c < C; ++c) active[c] = false;
-            for (int t = 0; t < lin.n; ++t) active[lin.col[t]] = true;
-            for (int i = 0; i < quat_count; ++i)
-                if (quat_start + i < C) active[quat_start + i] = true;
-            int c = 0;
-            while (c < C) {
-                if (active[c]) {
-                    ++c;
-                    continue;
-                }
-                int e = c;
-                while (e < C && !active[e]) ++e;
-                cudaMemsetAsync(base + (size_t)c * plane_floats, 0, (size_t)(e - c) * plane_floats * sizeof(float),
-                                stream);
-                c = e;
-            }
-        };
-        zero_inactive(grads->xyz_deform, basis->xyz, 0, 0, (size_t)3 * No);
-        zero_inactive(grads->rot_deform, basis->rotation, basis->quat.start,
-                      basis->quat.n_ctrl ? basis->quat.k + 1 : 0, (size_t)4 * No);
-    }
-
-    FusedBwdArgs a;
-    memset(&a, 0, sizeof(a));
-    a.m = *model;
-    a.g = *grads;
-    a.tb = *basis;
-    a.rp = rp;
-    a.view = cam->viewmatrix;
-    a.proj = cam->projmatrix;
-    a.campos = cam->campos;
-    a.radii = radii;
-    a.cov3D = gs.cov3D;
-    a.clamped = gs.clamped;
-    char* svp = svc;
     float4* saved4 = nullptr;
-    carve(svp, saved4, (size_t)N * 3);
-    a.saved = saved4;
-    a.grad_record = grad_record;
-    a.dL_dmeans2D = dL_dmeans2D;
-    a.dq_scratch = dq_scratch;
-    a.bg_scratch = bg_scratch;
+    carve(svc, saved4, (size_t)N * 3);
+    if ((st = run_blend_backward(cam, N, render_objmask, basis->has_flow != 0,
+                                 reinterpret_cast<const float4*>(gs.record), bs, is, capacity, img_opacity, dpix,
+                                 grad_record, stream)))
+        return st;
+    return run_per_gaussian_backward(cam, model, basis, radii, gs.cov3D, gs.clamped, saved4, grad_record, grads, 0,
+                                     dL_dmeans2D, dq_scratch, bg_scratch, stream);
+}
+
+/* ---- splat exchange: Gaussian-sharded front end / back end, view-sharded blend ------------------------ */
+
+size_t adgs_shard_state_bytes(int32_t N)
+{
+    // cov3D (6 floats) + clamped (1 byte) + saved (12 floats) per Gaussian of the shard, per view
+    const size_t n = (size_t)(N > 0 ? N : 0);
+    return n * 6 * sizeof(float) + n + n * kSavedFloats * sizeof(float) + 3 * 128 + 256;
+}
+
+struct ShardState {
+    float* cov3D;
+    uint8_t* clamped;
+    float4* saved;
+    static ShardState from_chunk(char*& c, size_t N)
     {
-        StageScope sc(kStagePerGaussianBwd, stream);
-        fused_backward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
-        count_launch(1);
+        ShardState s;
+        carve(c, s.cov3D, N * 6);
+        carve(c, s.clamped, N);
+        carve(c, s.saved, N * 3);
+        return s;
     }
-    if ((st = check_stage("fused backward", debug, stream))) return st;
-    if (No > 0) {
-        StageScope sc(kStageRotationBwd, stream);
-        rotation_backward_kernel<<<(No + 127) / 128, 128, 0, stream>>>(a);
-        count_launch(1);
-    }
-    if ((st = check_stage("rotation backward", debug, stream))) return st;
-    if (grads->background_deform && basis->background.n_cols > 0) {
-        count_launch(1);
-        background_finalize_kernel<<<1, 128, 0, stream>>>(a);
-        if ((st = check_stage("background finalize", debug, stream))) return st;
-    }
-    return ADGS_OK;
+};
+
+int adgs_shard_forward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
+                       int32_t render_objmask, const adgs_splats* out, char* shard_state, adgs_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st = validate_model(model, basis);
+    if (st) return st;
+    if ((st = check_render_args(cam))) return st;
+    const int N = model->N_scene + model->N_obj;
+    if (!out || !shard_state || N == 0 || out->P != N) return ADGS_ERR_ARG;
+    if (!out->record || !out->depth_keys || !out->tiles_touched || !out->radii) return ADGS_ERR_ARG;
+    char* c = shard_state;
+    ShardState ss = ShardState::from_chunk(c, (size_t)N);
+    SplatPtrs sp{reinterpret_cast<float4*>(out->record), out->depth_keys, out->tiles_touched, out->radii};
+    return run_per_gaussian_forward(cam, model, basis, render_objmask, nullptr, sp, ss.cov3D, ss.clamped, ss.saved,
+                                    stream);
+}
+
+int adgs_splats_forward(const adgs_camera* cam, const adgs_splats* splats, int32_t D_S, int32_t has_flow,
+                        const adgs_images* out, char* geometry, char* binning, int64_t capacity,
+                        adgs_alloc_fn binning_alloc, void* alloc_user, char* image, adgs_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st = check_render_args(cam);
+    if (st) return st;
+    if (!splats || !out || !geometry || !image || capacity < 0 || splats->P <= 0) return ADGS_ERR_ARG;
+    if (!binning && !binning_alloc) return ADGS_ERR_ARG;
+    if (!out->depth || !out->opacity || D_S < 0 || D_S > 1) return ADGS_ERR_ARG;
+    const int P = splats->P;
+    GeometryState gs = GeometryState::from_chunk(geometry, (size_t)P);
+    ImageState is = ImageState::from_chunk(image, cam->image_width, cam->image_height);
+    cudaMemsetAsync(gs.counters, 0, 32 * sizeof(uint32_t), stream);
+    // binning + blend read the per-Gaussian state from the caller's (gathered) arrays
+    gs.record = splats->record;
+    gs.depth_keys = splats->depth_keys;
+    gs.tiles_touched = splats->tiles_touched;
+    int R = 0;
+    st = bin_and_blend(cam, P, D_S, has_flow != 0, nullptr, out, splats->radii, gs, binning, binning_alloc, alloc_user,
+                       capacity, is, binning == nullptr, &R, stream);
+    return st ? st : R;
+}
+
+int adgs_splats_backward(const adgs_camera* cam, const adgs_splats* splats, int32_t D_S, int32_t has_flow,
+                         const char* binning, int64_t capacity, const char* image, const float* img_opacity,
+                         const adgs_image_grads* dpix, float* grad_record, adgs_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st = check_render_args(cam);
+    if (st) return st;
+    if (!splats || !binning || !image || !img_opacity || !dpix || !grad_record || capacity < 0 || splats->P <= 0)
+        return ADGS_ERR_ARG;
+    char* bc = const_cast<char*>(binning);
+    char* ic = const_cast<char*>(image);
+    BinningState bs = BinningState::from_chunk(bc, (size_t)capacity);
+    ImageState is = ImageState::from_chunk(ic, cam->image_width, cam->image_height);
+    return run_blend_backward(cam, splats->P, D_S, has_flow != 0, reinterpret_cast<const float4*>(splats->record), bs,
+                              is, capacity, img_opacity, dpix, grad_record, stream);
+}
+
+int adgs_shard_backward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
+                        const int32_t* radii, const char* shard_state, const float* grad_record,
+                        const adgs_model* grads, int32_t accumulate, float* dL_dmeans2D, char* scratch,
+                        adgs_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st = validate_model(model, basis);
+    if (st) return st;
+    if ((st = check_render_args(cam))) return st;
+    if (!radii || !shard_state || !grad_record || !grads || !scratch) return ADGS_ERR_ARG;
+    if (!grads->xyz || !grads->scaling || !grads->rotation || !grads->opacity || !grads->sh4) return ADGS_ERR_ARG;
+    const int N = model->N_scene + model->N_obj;
+    if (N == 0) return ADGS_ERR_ARG;
+    char* c = const_cast<char*>(shard_state);
+    ShardState ss = ShardState::from_chunk(c, (size_t)N);
+    char* sc = scratch;
+    float4* dq_scratch = nullptr;
+    float* bg_scratch = nullptr;
+    carve(sc, dq_scratch, (size_t)(model->N_obj > 0 ? model->N_obj : 1));
+    carve(sc, bg_scratch, 32);
+    return run_per_gaussian_backward(cam, model, basis, radii, ss.cov3D, ss.clamped, ss.saved, grad_record, grads,
+                                     accumulate, dL_dmeans2D, dq_scratch, bg_scratch, stream);
 }
 
 }  // extern "C"

@@ -233,6 +233,32 @@ class GaussianModel(nn.Module):
             out["gs_time"] = self.gs_time.reshape(-1, 1)
         return out
 
+    def shard(self, rank: int, world: int):
+        """Rank `rank`'s slice of the model for the splat-exchange multi-GPU path: contiguous blocks of
+        the scene and of the object Gaussians, padded to equal sizes across ranks with fully
+        transparent Gaussians (opacity logit -1e30 => alpha = 0: they contribute nothing anywhere)."""
+        ref = self.to_reference()
+        ns, no = -(-self.n_scene // world), -(-self.n_obj // world)
+
+        def cut(t, n_per, pad_value=0.0):
+            part = t[rank * n_per:(rank + 1) * n_per]
+            if part.shape[0] < n_per:
+                pad = torch.full((n_per - part.shape[0],) + tuple(t.shape[1:]), pad_value, dtype=t.dtype, device=t.device)
+                part = torch.cat([part, pad], dim=0)
+            return part.contiguous()
+
+        out = {}
+        for k, v in ref.items():
+            if k == "background_deform_param":
+                out[k] = v.clone()
+                continue
+            per = ns if (k.startswith("scene_") or k == "shs_deform_param_scene") else no
+            out[k] = cut(v, per, -1e30 if k.endswith("_opacity") else 0.0)
+        m = GaussianModel.from_reference(out, self.order_args, sh_degree=self.max_sh_degree,
+                                         use_time_mask=self.use_time_mask, device=self.xyz.device)
+        m.active_sh_degree = self.active_sh_degree
+        return m
+
     def hot_parameters(self):
         return [getattr(self, k) for k in PARAM_NAMES]
 

@@ -190,9 +190,27 @@ def run_ours(args):
         return ((res["render"], res["depth"], res["img_opacity"], res["img_flow"], res["img_semantic"]),
                 (c["color"], c["depth"][0], c["opacity"][0], c["flow"], c["semantic"]))
 
-    mv = MultiViewStep(model) if world > 1 else None
+    exchange = world > 1 and args.parallel == "exchange"
+    mv = MultiViewStep(model) if (world > 1 and not exchange) else None
+    ex = None
+    if exchange:
+        # Gaussian-sharded front/back end + all-to-all of splats (adgs_b200/parallel.py:SplatExchangeStep)
+        from adgs_b200.parallel import SplatExchangeStep
+        shard = model.shard(rank, world)
+        model_full = model
+        ex = SplatExchangeStep(shard)
+        all_views = []
+        for r in range(world):
+            c_r, t_r, f_r = view_for_rank(wl, r, device)
+            all_views.append((c_r, f_r))
+        cot_dict = {"color": cot["color"], "depth": cot["depth"], "opacity": cot["opacity"], "flow": cot["flow"],
+                    "semantic": cot["semantic"]}
+        del model_full
 
     def step():
+        if ex is not None:
+            ex.run(all_views, lambda v, r: cot_dict, pipe)
+            return None
         if mv is None:
             for p in params:
                 p.grad = None
@@ -239,7 +257,7 @@ def run_ours(args):
     # ---- roofline: per-stage CUDA events through the library hooks (rank 0) ------------------------
     roof, stage_ms, step_roof = None, None, None
     R = int(getattr(model, "_last_num_rendered", 0))
-    if rank == 0:
+    if True:
         import ctypes as C
         ns = lib.adgs_profile_num_stages()
         ms_buf = (C.c_float * ns)()
@@ -248,15 +266,13 @@ def run_ours(args):
         lib.adgs_profile_begin()
         prof_steps = max(3, min(args.steps, 10))
         for _ in range(prof_steps):
-            for p in params:
-                p.grad = None
-            res = render(cam, model, None, pipe, flow_pkg=flow_pkg, render_objmask=True)
-            outs, cots = outputs_and_cotangents(res, cot)
-            torch.autograd.backward(outs, cots)
+            step()      # every rank takes part (the step holds collectives when N > 1)
         torch.cuda.synchronize()
         lib.adgs_profile_end(ms_buf, cnt_buf)
         stage_ms = {lib.adgs_profile_stage_name(i).decode(): ms_buf[i] / prof_steps for i in range(ns)}
         R = int(getattr(model, "_last_num_rendered", R))
+        if ex is not None:
+            R = max(0, int((ex._capacity - 65536) / 1.3))
         total_b, per_stage = algorithmic_bytes(n_scene, n_obj, R, px)
         peak, peak_src = measured_hbm_peak()
         kernel_stages = {k: stage_ms[k] for k in ("per_gaussian_forward", "blend_forward", "blend_backward",
@@ -300,7 +316,30 @@ def run_ours(args):
 
     copy_stream = torch.cuda.Stream(device=device)
 
+    def e2e_step_exchange():
+        dcam = host_cam.to(device, non_blocking=True)
+        views_ = list(all_views)
+        views_[rank] = (cam._replace(world_view_transform=dcam[0:16].view(4, 4),
+                                     full_proj_transform=dcam[16:32].view(4, 4), camera_center=dcam[32:35]),
+                        all_views[rank][1])
+        with torch.cuda.stream(copy_stream):
+            flat = host_cot.to(device, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        box = {}
+
+        def cots(v, r):
+            torch.cuda.current_stream(device).wait_event(ready)
+            flat.record_stream(torch.cuda.current_stream(device))
+            box["res"] = r
+            return split_cot(flat)
+
+        ex.run(views_, cots, pipe)
+        return float(box["res"]["img_opacity"].mean().item())
+
     def e2e_step():
+        if ex is not None:
+            return e2e_step_exchange()
         # host -> device: camera matrices first (needed by the forward), cotangent planes on a copy
         # stream so that the PCIe transfer overlaps the forward; the backward waits for them.
         dcam = host_cam.to(device, non_blocking=True)
@@ -355,7 +394,9 @@ def run_ours(args):
                        "gaussians": wl["n"], "object_fraction": wl["obj_frac"], "control_points": 32,
                        "bspline_order": 5, "fourier_terms": 6, "sh_degree": 3, "flow": True, "objmask": True,
                        "inv_depth": True, "l2": "inputs (>1.5 GB of parameters per step) exceed the 126 MB L2",
-                       "parallelism": f"views sharded over {world} rank(s), flat-buffer NCCL all-reduce of parameter gradients"},
+                       "parallelism": (f"{world} rank(s); Gaussians sharded, views blended one per rank, NCCL all-to-all of "
+                                       "76-byte splats / 64-byte gradient records (no gradient all-reduce)" if exchange else
+                                       f"views sharded over {world} rank(s), flat-buffer NCCL all-reduce of parameter gradients")},
             "gaussians_per_s": round(gauss, 1),
             "e2e": e2e, "gpu_launches": round(launches, 1), "clocks": clocks,
             "roofline": roof, "step_roofline": step_roof, "stage_ms": {k: round(v, 4) for k, v in (stage_ms or {}).items()},
@@ -494,6 +535,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti-375x1242-1M", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parallel", default="exchange", choices=["exchange", "allreduce"],
+                    help="multi-GPU data path (N > 1): splat exchange (default) or replicated model + gradient all-reduce")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

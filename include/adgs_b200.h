@@ -331,6 +331,44 @@ ADGS_API int adgs_render_backward(const adgs_camera* cam, const adgs_model* mode
                          adgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Splat exchange (multi-GPU, no reference counterpart: the reference is single-GPU). The fused
+ * render split at its two natural seams so that Gaussians can be sharded across ranks while every
+ * view is blended on one rank:
+ *   adgs_shard_forward   trajectory + preprocess of one model shard for one view -> adgs_splats
+ *                        (the only state binning/blend need: 76 B per Gaussian) + shard-local
+ *                        backward state (adgs_shard_state_bytes);
+ *   adgs_splats_forward  binning + blend of any concatenation of adgs_splats (e.g. all shards of a view
+ *                        after an all-to-all); binning modes as in adgs_render_forward;
+ *   adgs_splats_backward blend backward -> packed 64-byte gradient records, one per splat;
+ *   adgs_shard_backward  per-Gaussian backward of a shard from its gradient records; `accumulate` != 0
+ *                        adds into `grads` (second and later views of a batch).
+ * adgs_render_forward/backward are exactly these four stages back to back on one device.
+ * scratch for adgs_shard_backward: adgs_render_scratch_bytes(0, N_obj).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct adgs_splats {
+    int32_t P;
+    int32_t _pad;
+    float* record;           /* (P,16) packed blend records */
+    uint32_t* depth_keys;    /* (P) float bits of view-space z, ~0 if culled; clobbered by the sort */
+    uint32_t* tiles_touched; /* (P) */
+    int32_t* radii;          /* (P) */
+} adgs_splats;
+
+ADGS_API size_t adgs_shard_state_bytes(int32_t N);
+ADGS_API int adgs_shard_forward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
+                       int32_t render_objmask, const adgs_splats* out, char* shard_state, adgs_stream_t stream);
+ADGS_API int adgs_splats_forward(const adgs_camera* cam, const adgs_splats* splats, int32_t D_S, int32_t has_flow,
+                        const adgs_images* out, char* geometry, char* binning, int64_t capacity,
+                        adgs_alloc_fn binning_alloc, void* alloc_user, char* image, adgs_stream_t stream);
+ADGS_API int adgs_splats_backward(const adgs_camera* cam, const adgs_splats* splats, int32_t D_S, int32_t has_flow,
+                         const char* binning, int64_t capacity, const char* image, const float* img_opacity,
+                         const adgs_image_grads* dpix, float* grad_record, adgs_stream_t stream);
+ADGS_API int adgs_shard_backward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
+                        const int32_t* radii, const char* shard_state, const float* grad_record,
+                        const adgs_model* grads, int32_t accumulate, float* dL_dmeans2D, char* scratch,
+                        adgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): cumulative number of kernels launched by the library, and
  * optional CUDA-event timing of each pipeline stage on the caller's stream.
  * adgs_profile_begin() arms it; adgs_profile_end() synchronises the recorded events and returns,

@@ -173,3 +173,54 @@ def test_multi_view_step_sums_view_gradients():
         assert Hh.rel_err(got[k], want[k]) <= 1e-5, k
         assert getattr(model, k).grad.data_ptr() == got[k].data_ptr()
     assert mv.stats.visible_count.max().item() <= 3 and mv.stats.visible_count.sum().item() > 0
+
+
+def test_splat_exchange_step_matches_multi_view_step():
+    """adgs_b200.parallel.SplatExchangeStep at world size 1 (all-to-all = identity): the four-stage
+    split (shard forward / splats forward / splats backward / shard backward with accumulation over
+    views) gives the images and the summed gradients of the monolithic path."""
+    from adgs_b200.parallel import MultiViewStep, SplatExchangeStep
+    order_args, ref, c = _scene(3000, 1000, "kitti75")
+    model = GaussianModel.from_reference({f: getattr(ref, f) for f in ref.FIELDS}, order_args)
+    cam = c["cam"]
+    cot = Hh.cotangents(c)
+    pipe = SimpleNamespace(inv_depth=True, debug=False, sync_free=True)
+
+    def vcam(t):
+        return SimpleNamespace(image_height=c["H"], image_width=c["W"], FoVx=cam.FoVx, FoVy=cam.FoVy,
+                               world_view_transform=cam.world_view_transform,
+                               full_proj_transform=cam.full_proj_transform, camera_center=cam.camera_center, time=t)
+
+    views = [(vcam(0.2), 0.25), (vcam(0.5), 0.55), (vcam(0.8), 0.75)]
+    render_fn = lambda v: render(v[0], model, None, pipe, flow_pkg=[v[1], None, None, None, None, None],
+                                 render_objmask=True)
+    cot_fn = lambda v, r: ((r["render"], r["depth"], r["img_opacity"], r["img_flow"], r["img_semantic"]),
+                           (cot["color"], cot["depth"][0], cot["opacity"][0], cot["flow"], cot["semantic"]))
+    mv = MultiViewStep(model)
+    want = {k: v.clone() for k, v in mv.run(views, render_fn, cot_fn).items()}
+    want_img = render_fn(views[2])["render"].detach().clone()
+
+    ex = SplatExchangeStep(model)
+    results, stats = ex.run(views, lambda v, r: cot, pipe)
+    assert len(results) == 3 and len(stats) == 3
+    assert torch.equal(results[2]["render"], want_img)
+    for k in want:
+        assert Hh.rel_err(getattr(model, k).grad, want[k]) <= 1e-5, k
+    # a second run must not accumulate into the first (accumulate flag resets per run)
+    ex.run(views, lambda v, r: cot, pipe)
+    for k in want:
+        assert Hh.rel_err(getattr(model, k).grad, want[k]) <= 1e-5, k
+
+
+def test_model_shards_partition_the_model():
+    order_args, ref, c = _scene(1001, 334, "kitti75")
+    model = GaussianModel.from_reference({f: getattr(ref, f) for f in ref.FIELDS}, order_args)
+    shards = [model.shard(r, 4) for r in range(4)]
+    assert all(s.n_scene == 251 and s.n_obj == 84 for s in shards)
+    xyz = torch.cat([s.xyz[:s.n_scene] for s in shards])[:1001]
+    assert torch.equal(xyz, model.xyz[:1001])
+    oxyz = torch.cat([s.xyz[s.n_scene:] for s in shards])[:334]
+    assert torch.equal(oxyz, model.xyz[1001:])
+    assert (shards[3].opacity[shards[3].n_scene - 3:shards[3].n_scene] < -1e29).all()   # padding is transparent
+    rd = torch.cat([s.rot_deform for s in shards], dim=1)[:, :334]
+    assert torch.equal(rd, model.rot_deform)
