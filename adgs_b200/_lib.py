@@ -235,6 +235,12 @@ SIGNATURES = {
                                        C.c_void_p, _P(ImageGrads), C.c_void_p, C.c_void_p]),
     "adgs_shard_backward": (C.c_int, [_P(Camera), _P(Model), _P(TimeBasis), C.c_void_p, C.c_void_p, C.c_void_p,
                                       _P(Model), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adgs_shard_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "adgs_shard_forward_multi": (C.c_int, [C.c_int32, _P(Camera), _P(Model), _P(TimeBasis), C.c_int32, _P(Splats),
+                                           _P(C.c_void_p), C.c_void_p]),
+    "adgs_shard_backward_multi": (C.c_int, [C.c_int32, _P(Camera), _P(Model), _P(TimeBasis), _P(C.c_void_p),
+                                            _P(C.c_void_p), _P(C.c_void_p), _P(Model), C.c_int32, _P(C.c_void_p),
+                                            C.c_void_p, C.c_void_p]),
     "adgs_launch_count": (C.c_ulonglong, []),
     "adgs_profile_begin": (C.c_int, []),
     "adgs_profile_num_stages": (C.c_int, []),

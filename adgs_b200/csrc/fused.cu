@@ -585,6 +585,461 @@ int validate_model(const adgs_model* m, const adgs_time_basis* tb)
 }
 
 
+// ------------------------------------------------------------------------------------------
+// Multi-view variants for the splat-exchange path: one launch evaluates a model shard for up to
+// kMaxViews views. Parameters are fetched from HBM once (re-reads of later views hit L1/L2), the
+// backward sums the per-view contributions in registers and writes every dense gradient once.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxViews = 8;
+
+struct ViewIO {
+    adgs_time_basis tb;
+    RasterParams rp;
+    const float* view;
+    const float* proj;
+    const float* campos;
+    int32_t* radii;
+    uint32_t* depth_keys;
+    uint32_t* tiles_touched;
+    float4* record;
+    float* cov3D;
+    uint8_t* clamped;
+    float4* saved;
+    const float* grad_record;  // backward only
+    float* dL_dmeans2D;        // backward only
+    float4* dq_scratch;        // backward only
+    float* bg_scratch;         // backward only
+};
+
+struct MultiViewArgs {
+    adgs_model m;
+    adgs_model g;
+    int render_objmask;
+    int num_views;
+    int accumulate;
+    int _pad;
+    ViewIO v[kMaxViews];
+};
+
+__global__ void __launch_bounds__(256, 2) shard_forward_multi_kernel(const __grid_constant__ MultiViewArgs a)
+{
+    __shared__ CamSmem cam;
+    __shared__ float s_bg[6];
+    const adgs_model& m = a.m;
+    const int N = m.N_scene + m.N_obj;
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = g < N;
+    const bool is_obj = valid && g >= m.N_scene;
+    const int j = g - m.N_scene;
+
+    // view-independent part: raw parameters -> activations, SH block
+    float x0[3] = {0.f, 0.f, 0.f}, scale[3] = {1.f, 1.f, 1.f}, sig = 0.f;
+    float4 qscene = make_float4(1.f, 0.f, 0.f, 0.f);
+    float sh[48];
+    const float4* sh4 = reinterpret_cast<const float4*>(m.sh4);
+    if (valid) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            x0[d] = m.xyz[3 * (size_t)g + d];
+            scale[d] = expf(m.scaling[3 * (size_t)g + d]);
+        }
+        sig = 1.0f / (1.0f + expf(-m.opacity[g]));
+        if (!is_obj) qscene = reinterpret_cast<const float4*>(m.rotation)[g];
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            const float4 v = __ldg(sh4 + (size_t)q * N + g);
+            sh[4 * q + 0] = v.x;
+            sh[4 * q + 1] = v.y;
+            sh[4 * q + 2] = v.z;
+            sh[4 * q + 3] = v.w;
+        }
+    }
+    const float dc0[3] = {sh[0], sh[1], sh[2]};
+
+    for (int vi = 0; vi < a.num_views; ++vi) {
+        const ViewIO& V = a.v[vi];
+        const adgs_time_basis& tb = V.tb;
+        __syncthreads();
+        if (threadIdx.x < 6) {
+            const int d = threadIdx.x % 3;
+            const bool second = threadIdx.x >= 3;
+            float v = 0.f;
+            for (int t = 0; t < tb.background.n; ++t)
+                v += m.background_deform[d * tb.background.n_cols + tb.background.col[t]] *
+                     (second ? tb.background.w1[t] : tb.background.w0[t]);
+            s_bg[threadIdx.x] = v;
+        }
+        load_camera(cam, V.view, V.proj, V.campos, nullptr);
+        if (!valid) continue;
+        const bool flow = tb.has_flow != 0;
+
+        float xt[3], xf[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) xt[d] = xf[d] = x0[d];
+        if (is_obj && tb.xyz.n) {
+            float d0[3] = {0.f, 0.f, 0.f}, d1[3] = {0.f, 0.f, 0.f};
+            lin_eval3_planar(m.xyz_deform, m.N_obj, j, tb.xyz, d0, d1, flow);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                xt[d] += d0[d];
+                xf[d] += d1[d];
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            xt[d] += s_bg[d];
+            xf[d] += s_bg[3 + d];
+        }
+        const float4 qraw = is_obj ? object_rotation_raw(m, tb, g, j, nullptr, nullptr) : qscene;
+        const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+        const float rot[4] = {qraw.x / qn, qraw.y / qn, qraw.z / qn, qraw.w / qn};
+        float op = sig;
+        if (is_obj && tb.use_time_mask) {
+            const float delta = tb.t - m.gs_time[j];
+            const float2 sgm = reinterpret_cast<const float2*>(m.gs_time_sigma)[j];
+            const float sigma = expf(delta < 0.0f ? sgm.x : sgm.y);
+            const float z = delta / sigma;
+            op *= expf(-0.5f * z * z);
+        }
+        float dc[3] = {dc0[0], dc0[1], dc0[2]};
+        if (tb.shs.n) {
+            const int Cs = tb.shs.n_cols;
+            const float* sd = m.shs_deform4;
+            for (int t = 0; t < tb.shs.n; ++t) {
+                const float w = tb.shs.w0[t];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int e = c * Cs + tb.shs.col[t];
+                    dc[c] += __ldg(sd + ((size_t)(e >> 2) * N + g) * 4 + (e & 3)) * w;
+                }
+            }
+        }
+        const float3 p = make_float3(xt[0], xt[1], xt[2]);
+        SplatGeom sg;
+        const bool visible = splat_geometry(p, scale, rot, nullptr, V.rp, cam.view, cam.proj, sg);
+        V.saved[(size_t)g * 3 + 0] = make_float4(xt[0], xt[1], xt[2], op);
+        V.saved[(size_t)g * 3 + 1] = make_float4(rot[0], rot[1], rot[2], rot[3]);
+        V.saved[(size_t)g * 3 + 2] = make_float4(dc[0], dc[1], dc[2], 0.f);
+        if (!visible) {
+            V.radii[g] = 0;
+            V.tiles_touched[g] = 0;
+            V.depth_keys[g] = 0xFFFFFFFFu;
+            continue;
+        }
+        sh[0] = dc[0];
+        sh[1] = dc[1];
+        sh[2] = dc[2];
+        float rgb[3];
+        uint32_t clamped;
+        sh_to_rgb(V.rp.sh_degree, p, cam.campos, sh, rgb, clamped);
+        V.clamped[g] = (uint8_t)clamped;
+        float2* c2 = reinterpret_cast<float2*>(V.cov3D + (size_t)g * 6);
+        c2[0] = make_float2(sg.cov3D[0], sg.cov3D[1]);
+        c2[1] = make_float2(sg.cov3D[2], sg.cov3D[3]);
+        c2[2] = make_float2(sg.cov3D[4], sg.cov3D[5]);
+        const float dfeat = V.rp.inv_depth ? (1.0f / (sg.depth + 0.0000001f)) : sg.depth;
+        const float sem0 = (a.render_objmask && is_obj) ? 1.f : 0.f;
+        float4* rec = V.record + (size_t)g * 4;
+        rec[0] = make_float4(sg.px, sg.py, sg.conic_x, sg.conic_y);
+        rec[1] = make_float4(sg.conic_z, op, rgb[0], rgb[1]);
+        rec[2] = make_float4(rgb[2], dfeat, flow ? xf[0] : 0.f, flow ? xf[1] : 0.f);
+        rec[3] = make_float4(flow ? xf[2] : 0.f, sem0, sg.depth, op > 0.f ? -__logf(255.f * op) : 1e30f);
+        V.radii[g] = sg.radius;
+        V.tiles_touched[g] = sg.tiles;
+        V.depth_keys[g] = __float_as_uint(sg.depth);
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) shard_backward_multi_kernel(const __grid_constant__ MultiViewArgs a)
+{
+    __shared__ CamSmem cam;
+    __shared__ float s_wshs[kMaxViews][ADGS_MAX_TERMS * 2];  // dense SH-deform weights per view and column
+    __shared__ float s_red[8][6];
+    const adgs_model& m = a.m;
+    const int N = m.N_scene + m.N_obj;
+    const int Cs = a.v[0].tb.shs.n_cols;
+    for (int i = threadIdx.x; i < kMaxViews * ADGS_MAX_TERMS * 2; i += blockDim.x) (&s_wshs[0][0])[i] = 0.f;
+    __syncthreads();
+    if (threadIdx.x < (unsigned)a.num_views) {
+        const adgs_lin_basis& b = a.v[threadIdx.x].tb.shs;
+        for (int t = 0; t < b.n; ++t) s_wshs[threadIdx.x][b.col[t]] += b.w0[t];
+    }
+
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = g < N;
+    const bool is_obj = valid && g >= m.N_scene;
+    const int j = g - m.N_scene;
+
+    float scale[3] = {1.f, 1.f, 1.f}, sig = 0.f;
+    float sh[48];
+    if (valid) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) scale[d] = expf(m.scaling[3 * (size_t)g + d]);
+        sig = 1.0f / (1.0f + expf(-m.opacity[g]));
+        const float4* sh4 = reinterpret_cast<const float4*>(m.sh4);
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            const float4 v = __ldg(sh4 + (size_t)q * N + g);
+            sh[4 * q + 0] = v.x;
+            sh[4 * q + 1] = v.y;
+            sh[4 * q + 2] = v.z;
+            sh[4 * q + 3] = v.w;
+        }
+    }
+    // accumulators over the views
+    float axyz[3] = {0.f, 0.f, 0.f}, ascale[3] = {0.f, 0.f, 0.f}, adq[4] = {0.f, 0.f, 0.f, 0.f};
+    float aop = 0.f, asig0 = 0.f, asig1 = 0.f;
+    float adsh[48];
+    float ddc[kMaxViews][3];
+#pragma unroll
+    for (int i = 0; i < 48; ++i) adsh[i] = 0.f;
+#pragma unroll
+    for (int v = 0; v < kMaxViews; ++v) ddc[v][0] = ddc[v][1] = ddc[v][2] = 0.f;
+    float4 rot_scene = make_float4(1.f, 0.f, 0.f, 0.f);
+
+#pragma unroll
+    for (int vi = 0; vi < kMaxViews; ++vi) {
+        if (vi >= a.num_views) break;
+        const ViewIO& V = a.v[vi];
+        const adgs_time_basis& tb = V.tb;
+        __syncthreads();
+        load_camera(cam, V.view, V.proj, V.campos, nullptr);
+        const bool flow = tb.has_flow != 0;
+        float dxt[3] = {0.f, 0.f, 0.f}, dfl[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+            const float4* gr = reinterpret_cast<const float4*>(V.grad_record) + (size_t)g * 4;
+            const float4 g0 = gr[0], g1 = gr[1], g2 = gr[2], g3 = gr[3];
+            if (V.dL_dmeans2D) {
+                V.dL_dmeans2D[3 * (size_t)g + 0] = g0.x;
+                V.dL_dmeans2D[3 * (size_t)g + 1] = g0.y;
+                V.dL_dmeans2D[3 * (size_t)g + 2] = 0.f;
+            }
+            const bool visible = V.radii[g] > 0;
+            const float4 sv0 = V.saved[(size_t)g * 3 + 0];
+            const float4 sv1 = V.saved[(size_t)g * 3 + 1];
+            const float rot[4] = {sv1.x, sv1.y, sv1.z, sv1.w};
+            if (!is_obj) rot_scene = sv1;
+            float dscale[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
+            if (flow) {
+                dfl[0] = g2.z;
+                dfl[1] = g2.w;
+                dfl[2] = g3.x;
+            }
+            if (visible) {
+                const float3 p = make_float3(sv0.x, sv0.y, sv0.z);
+                float cv[6], dcov[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) cv[i] = V.cov3D[(size_t)g * 6 + i];
+                const float3 dm = cov2d_bwd(p, V.rp, cv, cam.view, g0.z, g0.w, g1.x, dcov);
+                const float3 dm2 = mean_proj_depth_bwd(p, cam.view, cam.proj, g0.x, g0.y, g2.y, V.rp.inv_depth);
+                const float4 sv2 = V.saved[(size_t)g * 3 + 2];
+                sh[0] = sv2.x;
+                sh[1] = sv2.y;
+                sh[2] = sv2.z;
+                const float dcol[3] = {g1.z, g1.w, g2.x};
+                float dsh[48];
+                const float3 dm3 = sh_to_rgb_bwd(V.rp.sh_degree, p, cam.campos, sh, V.clamped[g], dcol, dsh);
+#pragma unroll
+                for (int i = 0; i < 48; ++i) adsh[i] += dsh[i];
+                ddc[vi][0] = dsh[0];
+                ddc[vi][1] = dsh[1];
+                ddc[vi][2] = dsh[2];
+                dxt[0] = dm.x + dm2.x + dm3.x;
+                dxt[1] = dm.y + dm2.y + dm3.y;
+                dxt[2] = dm.z + dm2.z + dm3.z;
+                cov3d_bwd(scale, V.rp.scale_modifier, rot, dcov, dscale, dq);
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                axyz[d] += dxt[d] + dfl[d];
+                ascale[d] += dscale[d] * scale[d];
+            }
+            {
+                const float dop = g1.y;
+                float mask = 1.f;
+                if (is_obj && tb.use_time_mask) {
+                    const float delta = tb.t - m.gs_time[j];
+                    const float2 sgm = reinterpret_cast<const float2*>(m.gs_time_sigma)[j];
+                    const bool neg = delta < 0.0f;
+                    const float sigma = expf(neg ? sgm.x : sgm.y);
+                    const float z = delta / sigma;
+                    mask = expf(-0.5f * z * z);
+                    const float dside = dop * sig * mask * z * z;
+                    if (neg) asig0 += dside; else asig1 += dside;
+                }
+                aop += dop * mask * sig * (1.f - sig);
+            }
+            if (!is_obj) {
+#pragma unroll
+                for (int d = 0; d < 4; ++d) adq[d] += dq[d];
+            } else {
+                V.dq_scratch[j] = make_float4(dq[0], dq[1], dq[2], dq[3]);
+            }
+            // windows differ between views: read-modify-write on planes the host zero-filled
+            if (is_obj && tb.xyz.n && a.g.xyz_deform) {
+                for (int t = 0; t < tb.xyz.n; ++t) {
+                    float* o = a.g.xyz_deform + ((size_t)tb.xyz.col[t] * 3) * m.N_obj + j;
+                    const float w0 = tb.xyz.w0[t], w1 = tb.xyz.w1[t];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) o[(size_t)d * m.N_obj] += dxt[d] * w0 + dfl[d] * w1;
+                }
+            }
+        }
+        if (tb.background.n) {
+            float r[6] = {dxt[0], dxt[1], dxt[2], dfl[0], dfl[1], dfl[2]};
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) r[i] += __shfl_xor_sync(0xffffffffu, r[i], off);
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            if (lane == 0)
+#pragma unroll
+                for (int i = 0; i < 6; ++i) s_red[warp][i] = r[i];
+            __syncthreads();
+            if (threadIdx.x < 6) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
+                if (s != 0.f) atomicAdd(V.bg_scratch + threadIdx.x, s);
+            }
+        }
+    }
+
+    if (!valid) return;
+    const int acc = a.accumulate;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        put(a.g.xyz + 3 * (size_t)g + d, axyz[d], acc);
+        put(a.g.scaling + 3 * (size_t)g + d, ascale[d], acc);
+    }
+    float4* gsh4 = reinterpret_cast<float4*>(a.g.sh4);
+#pragma unroll
+    for (int q = 0; q < 12; ++q)
+        put4(gsh4 + (size_t)q * N + g, make_float4(adsh[4 * q], adsh[4 * q + 1], adsh[4 * q + 2], adsh[4 * q + 3]), acc);
+    if (a.g.shs_deform4 && Cs > 0) {
+        const int nq = (3 * Cs + 3) / 4;
+        float4* gsd = reinterpret_cast<float4*>(a.g.shs_deform4);
+        for (int q = 0; q < nq; ++q) {
+            float v[4];
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+                const int e = 4 * q + e4;
+                const int c = e / Cs;
+                float sum = 0.f;
+                if (c < 3) {
+#pragma unroll
+                    for (int vv = 0; vv < kMaxViews; ++vv)
+                        if (vv < a.num_views) sum += (c == 0 ? ddc[vv][0] : (c == 1 ? ddc[vv][1] : ddc[vv][2])) * s_wshs[vv][e - c * Cs];
+                }
+                v[e4] = sum;
+            }
+            put4(gsd + (size_t)q * N + g, make_float4(v[0], v[1], v[2], v[3]), acc);
+        }
+    }
+    put(a.g.opacity + g, aop, acc);
+    if (is_obj && a.g.gs_time_sigma) put2(reinterpret_cast<float2*>(a.g.gs_time_sigma) + j, make_float2(asig0, asig1), acc);
+    if (!is_obj) {
+        const float4 qraw = reinterpret_cast<const float4*>(m.rotation)[g];
+        const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+        put4(reinterpret_cast<float4*>(a.g.rotation) + g,
+             normalize4_bwd(rot_scene, qn, make_float4(adq[0], adq[1], adq[2], adq[3])), acc);
+    }
+}
+
+// Rotation chain of the object Gaussians for every view of the batch; the control-quaternion windows
+// differ between views, so the (host zero-filled) planes are accumulated with read-modify-write.
+__global__ void __launch_bounds__(128) rotation_backward_multi_kernel(const __grid_constant__ MultiViewArgs a)
+{
+    const adgs_model& m = a.m;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m.N_obj) return;
+    const int g = m.N_scene + j;
+    const float4* rd = reinterpret_cast<const float4*>(m.rot_deform);
+    float4* grd = reinterpret_cast<float4*>(a.g.rot_deform);
+    float4 grot = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int vi = 0; vi < a.num_views; ++vi) {
+        const ViewIO& V = a.v[vi];
+        const adgs_time_basis& tb = V.tb;
+        float4 qraw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tb.quat.n_ctrl == 0) qraw = reinterpret_cast<const float4*>(m.rotation)[g];
+        for (int t = 0; t < tb.rotation.n; ++t) {
+            const float4 p = __ldg(rd + (size_t)tb.rotation.col[t] * m.N_obj + j);
+            const float w = tb.rotation.w0[t];
+            qraw.x += p.x * w;
+            qraw.y += p.y * w;
+            qraw.z += p.z * w;
+            qraw.w += p.w * w;
+        }
+        Quat qt[ADGS_MAX_QUAT_ORDER + 1], P[ADGS_MAX_QUAT_ORDER + 1], E[ADGS_MAX_QUAT_ORDER + 1];
+        float3 om[ADGS_MAX_QUAT_ORDER + 1];
+        float norms[ADGS_MAX_QUAT_ORDER + 1];
+        const int k = tb.quat.k;
+        if (tb.quat.n_ctrl != 0) {
+#pragma unroll
+            for (int i = 0; i <= ADGS_MAX_QUAT_ORDER; ++i) {
+                norms[i] = 1.f;
+                if (i <= k) {
+                    qt[i] = ctrl_quat(__ldg(rd + (size_t)(tb.quat.start + i) * m.N_obj + j), norms[i]);
+                } else {
+                    qt[i] = Quat{0.f, 0.f, 0.f, 1.f};
+                }
+            }
+            const Quat r = quat_spline_cached(qt, k, tb.quat.cum, P, E, om);
+            qraw.x += r.w;
+            qraw.y += r.x;
+            qraw.z += r.y;
+            qraw.w += r.z;
+        }
+        const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+        const float4 qhat = make_float4(qraw.x / qn, qraw.y / qn, qraw.z / qn, qraw.w / qn);
+        const float4 graw = normalize4_bwd(qhat, qn, V.dq_scratch[j]);  // wxyz
+        if (tb.quat.n_ctrl == 0) {
+            grot.x += graw.x;
+            grot.y += graw.y;
+            grot.z += graw.z;
+            grot.w += graw.w;
+        }
+        if (!grd) continue;
+        for (int t = 0; t < tb.rotation.n; ++t) {
+            const float w = tb.rotation.w0[t];
+            put4(grd + (size_t)tb.rotation.col[t] * m.N_obj + j,
+                 make_float4(graw.x * w, graw.y * w, graw.z * w, graw.w * w), 1);
+        }
+        if (tb.quat.n_ctrl != 0) {
+            Quat gqt[ADGS_MAX_QUAT_ORDER + 1];
+            quat_spline_bwd(qt, k, tb.quat.cum, P, E, om, Quat{graw.y, graw.z, graw.w, graw.x}, gqt);
+#pragma unroll
+            for (int i = 0; i <= ADGS_MAX_QUAT_ORDER; ++i) {
+                if (i <= k) {
+                    const float4 nq = make_float4(qt[i].w, qt[i].x, qt[i].y, qt[i].z);
+                    const float4 gg = make_float4(gqt[i].w, gqt[i].x, gqt[i].y, gqt[i].z);
+                    put4(grd + (size_t)(tb.quat.start + i) * m.N_obj + j, normalize4_bwd(nq, norms[i], gg), 1);
+                }
+            }
+        }
+    }
+    put4(reinterpret_cast<float4*>(a.g.rotation) + g, grot, a.accumulate);
+}
+
+// background gradient from the per-view sums
+__global__ void background_finalize_multi_kernel(const __grid_constant__ MultiViewArgs a)
+{
+    float* out = a.g.background_deform;
+    if (!out) return;
+    const int C = a.v[0].tb.background.n_cols;
+    if (!a.accumulate)
+        for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) out[i] = 0.f;
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int d = threadIdx.x;
+        for (int vi = 0; vi < a.num_views; ++vi) {
+            const adgs_lin_basis& b = a.v[vi].tb.background;
+            const float* sums = a.v[vi].bg_scratch;
+            for (int t = 0; t < b.n; ++t) out[d * C + b.col[t]] += sums[d] * b.w0[t] + sums[3 + d] * b.w1[t];
+        }
+    }
+}
+
 // ---- host-side stages shared by the single-GPU entry points and the splat-exchange entry points ----
 
 struct SplatPtrs {  // per-Gaussian per-view state consumed by binning + blend
@@ -965,6 +1420,133 @@ int adgs_shard_backward(const adgs_camera* cam, const adgs_model* model, const a
     carve(sc, bg_scratch, 32);
     return run_per_gaussian_backward(cam, model, basis, radii, ss.cov3D, ss.clamped, ss.saved, grad_record, grads,
                                      accumulate, dL_dmeans2D, dq_scratch, bg_scratch, stream);
+}
+
+/* multi-view variants: one launch per stage for all views of a round (adgs_b200/parallel.py) */
+int adgs_shard_forward_multi(int32_t num_views, const adgs_camera* cams, const adgs_model* model,
+                             const adgs_time_basis* bases, int32_t render_objmask, const adgs_splats* outs,
+                             char* const* shard_states, adgs_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (num_views < 1 || num_views > kMaxViews || !cams || !bases || !outs || !shard_states) return ADGS_ERR_ARG;
+    const int N = model ? model->N_scene + model->N_obj : 0;
+    if (N == 0) return ADGS_ERR_ARG;
+    static MultiViewArgs a;  // 17 KB: keep it off the stack
+    memset(&a, 0, sizeof(a));
+    a.m = *model;
+    a.render_objmask = render_objmask;
+    a.num_views = num_views;
+    for (int v = 0; v < num_views; ++v) {
+        int st = validate_model(model, &bases[v]);
+        if (st) return st;
+        if ((st = check_render_args(&cams[v]))) return st;
+        if (outs[v].P != N || !outs[v].record || !outs[v].depth_keys || !outs[v].tiles_touched || !outs[v].radii ||
+            !shard_states[v])
+            return ADGS_ERR_ARG;
+        char* c = shard_states[v];
+        ShardState ss = ShardState::from_chunk(c, (size_t)N);
+        ViewIO& V = a.v[v];
+        V.tb = bases[v];
+        V.rp = make_raster_params(&cams[v]);
+        V.view = cams[v].viewmatrix;
+        V.proj = cams[v].projmatrix;
+        V.campos = cams[v].campos;
+        V.radii = outs[v].radii;
+        V.depth_keys = outs[v].depth_keys;
+        V.tiles_touched = outs[v].tiles_touched;
+        V.record = reinterpret_cast<float4*>(outs[v].record);
+        V.cov3D = ss.cov3D;
+        V.clamped = ss.clamped;
+        V.saved = ss.saved;
+    }
+    {
+        StageScope sc(kStagePerGaussianFwd, stream);
+        shard_forward_multi_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+        count_launch(1);
+    }
+    return check_stage("shard forward (multi-view)", cams[0].debug != 0, stream);
+}
+
+int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cams, const adgs_model* model,
+                              const adgs_time_basis* bases, const int32_t* const* radii,
+                              char* const* shard_states, const float* const* grad_records,
+                              const adgs_model* grads, int32_t accumulate, float* const* dL_dmeans2D,
+                              char* scratch, adgs_stream_t stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (num_views < 1 || num_views > kMaxViews || !cams || !bases || !radii || !shard_states || !grad_records ||
+        !grads || !scratch)
+        return ADGS_ERR_ARG;
+    if (!grads->xyz || !grads->scaling || !grads->rotation || !grads->opacity || !grads->sh4) return ADGS_ERR_ARG;
+    const int N = model ? model->N_scene + model->N_obj : 0;
+    if (N == 0) return ADGS_ERR_ARG;
+    const int No = model->N_obj;
+    const bool debug = cams[0].debug != 0;
+    static MultiViewArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = *model;
+    a.g = *grads;
+    a.num_views = num_views;
+    a.accumulate = accumulate;
+    // scratch: per view dq (N_obj float4) + 32 floats of background sums
+    char* sc = scratch;
+    for (int v = 0; v < num_views; ++v) {
+        int st = validate_model(model, &bases[v]);
+        if (st) return st;
+        if ((st = check_render_args(&cams[v]))) return st;
+        if (!radii[v] || !shard_states[v] || !grad_records[v]) return ADGS_ERR_ARG;
+        char* c = shard_states[v];
+        ShardState ss = ShardState::from_chunk(c, (size_t)N);
+        ViewIO& V = a.v[v];
+        V.tb = bases[v];
+        V.rp = make_raster_params(&cams[v]);
+        V.view = cams[v].viewmatrix;
+        V.proj = cams[v].projmatrix;
+        V.campos = cams[v].campos;
+        V.radii = const_cast<int32_t*>(radii[v]);
+        V.cov3D = ss.cov3D;
+        V.clamped = ss.clamped;
+        V.saved = ss.saved;
+        V.grad_record = grad_records[v];
+        V.dL_dmeans2D = dL_dmeans2D ? dL_dmeans2D[v] : nullptr;
+        carve(sc, V.dq_scratch, (size_t)(No > 0 ? No : 1));
+        carve(sc, V.bg_scratch, 32);
+    }
+    {
+        StageScope scope(kStageFills, stream);
+        for (int v = 0; v < num_views; ++v) cudaMemsetAsync(a.v[v].bg_scratch, 0, 32 * sizeof(float), stream);
+        if (!accumulate && No > 0) {
+            // windows differ between views and are accumulated with += : start from all-zero planes
+            if (grads->xyz_deform && bases[0].xyz.n_cols > 0)
+                cudaMemsetAsync(grads->xyz_deform, 0, (size_t)bases[0].xyz.n_cols * 3 * No * sizeof(float), stream);
+            if (grads->rot_deform && bases[0].rotation.n_cols > 0)
+                cudaMemsetAsync(grads->rot_deform, 0, (size_t)bases[0].rotation.n_cols * 4 * No * sizeof(float), stream);
+        }
+    }
+    int st;
+    {
+        StageScope scope(kStagePerGaussianBwd, stream);
+        shard_backward_multi_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+        count_launch(1);
+    }
+    if ((st = check_stage("shard backward (multi-view)", debug, stream))) return st;
+    if (No > 0) {
+        StageScope scope(kStageRotationBwd, stream);
+        rotation_backward_multi_kernel<<<(No + 127) / 128, 128, 0, stream>>>(a);
+        count_launch(1);
+    }
+    if ((st = check_stage("rotation backward (multi-view)", debug, stream))) return st;
+    if (grads->background_deform && bases[0].background.n_cols > 0) {
+        background_finalize_multi_kernel<<<1, 128, 0, stream>>>(a);
+        count_launch(1);
+        if ((st = check_stage("background finalize (multi-view)", debug, stream))) return st;
+    }
+    return ADGS_OK;
+}
+
+size_t adgs_shard_scratch_bytes(int32_t num_views, int32_t N_obj)
+{
+    return (size_t)(num_views > 0 ? num_views : 1) * ((size_t)(N_obj > 0 ? N_obj : 1) * 16 + 128 + 256) + 256;
 }
 
 }  // extern "C"

@@ -199,114 +199,136 @@ class SplatExchangeStep:
         dist.all_to_all_single(recv, send, group=self.group)
         return recv
 
-    def run(self, views, cotangent_fn, pipe):
+    def run(self, views, cotangent_fn, pipe, views_per_rank=1):
+        """One iteration over `views` (a multiple of world_size * views_per_rank entries). In every round
+        rank r blends views [r*k, (r+1)*k) of the round's world_size*k views (k = views_per_rank <= 8/G)."""
         import ctypes as C
         L, lib, m = self.L, self.lib, self.model
-        G, n, dev = self.world, m.get_pts_num, m.xyz.device
-        assert len(views) % G == 0, "the batch must hold a multiple of world_size views"
+        G, k, n, dev = self.world, int(views_per_rank), m.get_pts_num, m.xyz.device
+        V = G * k
+        assert 1 <= V <= 8, "at most 8 views per round (ADGS_MAX_VIEWS)"
+        assert len(views) % V == 0, "the batch must hold a multiple of world_size * views_per_rank views"
         stream = torch.cuda.current_stream(dev).cuda_stream
         results, stats = [], []
         first = True
-        for rnd in range(len(views) // G):
-            batch = views[rnd * G:(rnd + 1) * G]
+        o = dict(dtype=torch.float32, device=dev)
+        D_S = 1 if self.render_objmask else 0
+        for rnd in range(len(views) // V):
+            batch = views[rnd * V:(rnd + 1) * V]
             keep = []
-            # ---- front end of my shard for every view of the round ------------------------------
-            rec = torch.empty((G, n, 16), dtype=torch.float32, device=dev)
-            keys = torch.empty((G, n), dtype=torch.int32, device=dev)
-            tiles = torch.empty((G, n), dtype=torch.int32, device=dev)
-            radii = torch.empty((G, n), dtype=torch.int32, device=dev)
-            state = torch.empty((G, lib.adgs_shard_state_bytes(n)), dtype=torch.uint8, device=dev)
-            cams, bases = [], []
             with torch.cuda.device(dev):
-                for v, (cam, flow_t) in enumerate(batch):
-                    cc = self._camera(cam, pipe, keep)
-                    tb = m.time_basis(cam.time, flow_t)
-                    cams.append(cc)
-                    bases.append(tb)
-                    sp = L.Splats(P=n, _pad=0, record=rec[v].data_ptr(), depth_keys=keys[v].data_ptr(),
-                                  tiles_touched=tiles[v].data_ptr(), radii=radii[v].data_ptr())
-                    L.check(lib.adgs_shard_forward(C.byref(cc), C.byref(m.c_model()), C.byref(tb),
-                                                   int(self.render_objmask), C.byref(sp), state[v].data_ptr(), stream),
-                            "shard_forward")
-                # ---- splats of view v travel to rank v ---------------------------------------------
-                r_rec, r_keys = self._all_to_all(rec), self._all_to_all(keys)
-                r_tiles, r_radii = self._all_to_all(tiles), self._all_to_all(radii)
-                # ---- bin + blend my view ---------------------------------------------------------
-                cam, flow_t = batch[self.rank]
-                cc, tb = cams[self.rank], bases[self.rank]
-                P, H, W = G * n, int(cam.image_height), int(cam.image_width)
-                o = dict(dtype=torch.float32, device=dev)
-                img = dict(color=torch.empty((3, H, W), **o), depth=torch.empty((1, H, W), **o),
-                           opacity=torch.empty((1, H, W), **o), flow=torch.empty((3, H, W), **o),
-                           semantic=torch.empty((1 if self.render_objmask else 0, H, W), **o))
-                images = L.Images(color=L.ptr(img["color"]), depth=L.ptr(img["depth"]), opacity=L.ptr(img["opacity"]),
-                                  flow=L.ptr(img["flow"]), semantic=L.ptr(img["semantic"]), radii=None)
-                splats = L.Splats(P=P, _pad=0, record=r_rec.data_ptr(), depth_keys=r_keys.data_ptr(),
-                                  tiles_touched=r_tiles.data_ptr(), radii=r_radii.data_ptr())
-                geom = torch.empty((lib.adgs_geometry_bytes(P),), dtype=torch.uint8, device=dev)
-                imgbuf = torch.empty((lib.adgs_image_bytes(W, H),), dtype=torch.uint8, device=dev)
-                has_flow = int(flow_t is not None)
-                D_S = 1 if self.render_objmask else 0
-                sync_free = bool(getattr(pipe, "sync_free", True)) and self._capacity > 0
-                if sync_free:
-                    capacity = self._capacity
-                    binning = torch.empty((lib.adgs_binning_bytes(capacity),), dtype=torch.uint8, device=dev)
-                    L.check(lib.adgs_splats_forward(C.byref(cc), C.byref(splats), D_S, has_flow, C.byref(images),
-                                                    L.ptr(geom), L.ptr(binning), capacity, L.ALLOC_FN(), None,
-                                                    L.ptr(imgbuf), stream), "splats_forward")
-                    counters = m._pinned_counters()
-                    L.check(lib.adgs_read_counters(L.ptr(geom), P, counters.data_ptr(), stream), "read_counters")
-                    ev = torch.cuda.Event()
-                    ev.record(torch.cuda.current_stream(dev))
-                else:
-                    holder = {}
+                # ---- front end of my shard for every view of the round: ONE launch ---------------------
+                rec = torch.empty((V, n, 16), **o)
+                keys = torch.empty((V, n), dtype=torch.int32, device=dev)
+                tiles = torch.empty((V, n), dtype=torch.int32, device=dev)
+                radii = torch.empty((V, n), dtype=torch.int32, device=dev)
+                state = torch.empty((V, lib.adgs_shard_state_bytes(n)), dtype=torch.uint8, device=dev)
+                cams = [self._camera(cam, pipe, keep) for cam, _ in batch]
+                bases = [m.time_basis(cam.time, flow_t) for cam, flow_t in batch]
+                cam_arr = (L.Camera * V)(*cams)
+                basis_arr = (L.TimeBasis * V)(*bases)
+                splat_arr = (L.Splats * V)(*[L.Splats(P=n, _pad=0, record=rec[v].data_ptr(),
+                                                      depth_keys=keys[v].data_ptr(), tiles_touched=tiles[v].data_ptr(),
+                                                      radii=radii[v].data_ptr()) for v in range(V)])
+                state_arr = (C.c_void_p * V)(*[state[v].data_ptr() for v in range(V)])
+                cmodel = m.c_model()
+                L.check(lib.adgs_shard_forward_multi(V, cam_arr, C.byref(cmodel), basis_arr, int(self.render_objmask),
+                                                     splat_arr, state_arr, stream), "shard_forward_multi")
+                # ---- splats of view v travel to the rank that blends it (chunk d of dim 0 -> rank d) ------
+                r_rec = self._all_to_all(rec).view(G, k, n, 16)
+                r_keys = self._all_to_all(keys).view(G, k, n)
+                r_tiles = self._all_to_all(tiles).view(G, k, n)
+                r_radii = self._all_to_all(radii).view(G, k, n)
+                gback = torch.empty((G, k, n, 16), **o)
+                P = G * n
+                for i in range(k):
+                    v_glob = self.rank * k + i
+                    cam, flow_t = batch[v_glob]
+                    cc = cams[v_glob]
+                    H, W = int(cam.image_height), int(cam.image_width)
+                    # all shards of my i-th view, rank-major (a plain view when k == 1)
+                    s_rec = r_rec[:, i].reshape(P, 16)
+                    s_keys = r_keys[:, i].reshape(P)
+                    if s_keys.data_ptr() == keys.data_ptr():
+                        s_keys = s_keys.clone()          # G == k == 1: keep the front end's keys intact
+                    s_tiles = r_tiles[:, i].reshape(P)
+                    s_radii = r_radii[:, i].reshape(P)
+                    img = dict(color=torch.empty((3, H, W), **o), depth=torch.empty((1, H, W), **o),
+                               opacity=torch.empty((1, H, W), **o), flow=torch.empty((3, H, W), **o),
+                               semantic=torch.empty((D_S, H, W), **o))
+                    images = L.Images(color=L.ptr(img["color"]), depth=L.ptr(img["depth"]),
+                                      opacity=L.ptr(img["opacity"]), flow=L.ptr(img["flow"]),
+                                      semantic=L.ptr(img["semantic"]), radii=None)
+                    splats = L.Splats(P=P, _pad=0, record=s_rec.data_ptr(), depth_keys=s_keys.data_ptr(),
+                                      tiles_touched=s_tiles.data_ptr(), radii=s_radii.data_ptr())
+                    geom = torch.empty((lib.adgs_geometry_bytes(P),), dtype=torch.uint8, device=dev)
+                    imgbuf = torch.empty((lib.adgs_image_bytes(W, H),), dtype=torch.uint8, device=dev)
+                    has_flow = int(flow_t is not None)
+                    sync_free = bool(getattr(pipe, "sync_free", True)) and self._capacity > 0
+                    if sync_free:
+                        capacity = self._capacity
+                        binning = torch.empty((lib.adgs_binning_bytes(capacity),), dtype=torch.uint8, device=dev)
+                        L.check(lib.adgs_splats_forward(C.byref(cc), C.byref(splats), D_S, has_flow, C.byref(images),
+                                                        L.ptr(geom), L.ptr(binning), capacity, L.ALLOC_FN(), None,
+                                                        L.ptr(imgbuf), stream), "splats_forward")
+                        counters = m._pinned_counters()
+                        L.check(lib.adgs_read_counters(L.ptr(geom), P, counters.data_ptr(), stream), "read_counters")
+                        ev = torch.cuda.Event()
+                        ev.record(torch.cuda.current_stream(dev))
+                    else:
+                        holder = {}
 
-                    def _alloc(nbytes, _u, holder=holder):
-                        holder["b"] = torch.empty((int(nbytes),), dtype=torch.uint8, device=dev)
-                        return holder["b"].data_ptr()
+                        def _alloc(nbytes, _u, holder=holder):
+                            holder["b"] = torch.empty((int(nbytes),), dtype=torch.uint8, device=dev)
+                            return holder["b"].data_ptr()
 
-                    cb = L.ALLOC_FN(_alloc)
-                    R = L.check(lib.adgs_splats_forward(C.byref(cc), C.byref(splats), D_S, has_flow, C.byref(images),
-                                                        L.ptr(geom), None, 0, cb, None, L.ptr(imgbuf), stream),
-                                "splats_forward")
-                    binning, capacity = holder["b"], int(R)
-                    self._capacity = max(self._capacity, int(1.3 * R) + 65536)
-                    counters = ev = None
-                res = {"render": img["color"], "depth": img["depth"][0], "img_opacity": img["opacity"][0],
-                       "img_flow": img["flow"] if has_flow else None,
-                       "img_semantic": img["semantic"] if self.render_objmask else None, "radii": r_radii.view(-1)}
-                results.append(res)
-                # ---- backward: blend on my view, gradient records back to the owners -------------------
-                cot = cotangent_fn((cam, flow_t), res)
-                ct = {k: (None if cot.get(k) is None else cot[k].contiguous()) for k in
-                      ("color", "depth", "opacity", "flow", "semantic")}
-                ig = L.ImageGrads(dL_dcolor=L.ptr(ct["color"]), dL_ddepth=L.ptr(ct["depth"]), dL_dflow=L.ptr(ct["flow"]),
-                                  dL_dsemantic=L.ptr(ct["semantic"]), dL_dopacity=L.ptr(ct["opacity"]))
-                if ev is not None:
-                    ev.synchronize()
-                    self._capacity = max(self._capacity, int(1.3 * int(counters[0])) + 65536)
-                    if bool(counters[1]) or int(counters[0]) > capacity:
-                        raise RuntimeError("adgs_b200: binning arena overflow in a sync-free splat-exchange step; "
-                                           "re-run the step (the arena has been enlarged)")
-                grec = torch.empty((G, n, 16), dtype=torch.float32, device=dev)
-                L.check(lib.adgs_splats_backward(C.byref(cc), C.byref(splats), D_S, has_flow, L.ptr(binning),
-                                                 int(capacity), L.ptr(imgbuf), L.ptr(img["opacity"]), C.byref(ig),
-                                                 grec.data_ptr(), stream), "splats_backward")
-                r_grec = self._all_to_all(grec)
-                # ---- per-Gaussian backward of my shard, one view after the other ----------------------
-                scratch = torch.empty((lib.adgs_render_scratch_bytes(0, m.n_obj),), dtype=torch.uint8, device=dev)
+                        cb = L.ALLOC_FN(_alloc)
+                        R = L.check(lib.adgs_splats_forward(C.byref(cc), C.byref(splats), D_S, has_flow,
+                                                            C.byref(images), L.ptr(geom), None, 0, cb, None,
+                                                            L.ptr(imgbuf), stream), "splats_forward")
+                        binning, capacity = holder["b"], int(R)
+                        self._capacity = max(self._capacity, int(1.3 * R) + 65536)
+                        counters = ev = None
+                    res = {"render": img["color"], "depth": img["depth"][0], "img_opacity": img["opacity"][0],
+                           "img_flow": img["flow"] if has_flow else None,
+                           "img_semantic": img["semantic"] if self.render_objmask else None, "radii": s_radii}
+                    results.append(res)
+                    # ---- blend backward of my view -> gradient records for every shard ------------------
+                    cot = cotangent_fn((cam, flow_t), res)
+                    ct = {kk: (None if cot.get(kk) is None else cot[kk].contiguous()) for kk in
+                          ("color", "depth", "opacity", "flow", "semantic")}
+                    ig = L.ImageGrads(dL_dcolor=L.ptr(ct["color"]), dL_ddepth=L.ptr(ct["depth"]),
+                                      dL_dflow=L.ptr(ct["flow"]), dL_dsemantic=L.ptr(ct["semantic"]),
+                                      dL_dopacity=L.ptr(ct["opacity"]))
+                    if ev is not None:
+                        ev.synchronize()
+                        self._capacity = max(self._capacity, int(1.3 * int(counters[0])) + 65536)
+                        if bool(counters[1]) or int(counters[0]) > capacity:
+                            raise RuntimeError("adgs_b200: binning arena overflow in a sync-free splat-exchange "
+                                               "step; re-run the step (the arena has been enlarged)")
+                    grec = gback[:, 0].view(P, 16) if k == 1 else torch.empty((P, 16), **o)
+                    L.check(lib.adgs_splats_backward(C.byref(cc), C.byref(splats), D_S, has_flow, L.ptr(binning),
+                                                     int(capacity), L.ptr(imgbuf), L.ptr(img["opacity"]), C.byref(ig),
+                                                     grec.data_ptr(), stream), "splats_backward")
+                    if k > 1:
+                        gback[:, i] = grec.view(G, n, 16)
+                # ---- gradient records back to the owners; per-Gaussian backward of my shard: ONE launch ----
+                r_grec = self._all_to_all(gback.view(V, n, 16))
+                scratch = torch.empty((lib.adgs_shard_scratch_bytes(V, m.n_obj),), dtype=torch.uint8, device=dev)
                 gm = m.c_model_from(self.grads, with_time=False)
-                for v in range(G):
-                    d2 = torch.empty((n, 3), dtype=torch.float32, device=dev)
-                    L.check(lib.adgs_shard_backward(C.byref(cams[v]), C.byref(m.c_model()), C.byref(bases[v]),
-                                                    radii[v].data_ptr(), state[v].data_ptr(), r_grec[v].data_ptr(),
-                                                    C.byref(gm), int(not first), d2.data_ptr(), L.ptr(scratch), stream),
-                            "shard_backward")
-                    first = False
-                    stats.append((d2, radii[v]))
+                d2 = torch.empty((V, n, 3), **o)
+                radii_arr = (C.c_void_p * V)(*[radii[v].data_ptr() for v in range(V)])
+                grec_arr = (C.c_void_p * V)(*[r_grec[v].data_ptr() for v in range(V)])
+                d2_arr = (C.c_void_p * V)(*[d2[v].data_ptr() for v in range(V)])
+                L.check(lib.adgs_shard_backward_multi(V, cam_arr, C.byref(cmodel), basis_arr, radii_arr, state_arr,
+                                                      grec_arr, C.byref(gm), int(not first), d2_arr, L.ptr(scratch),
+                                                      stream), "shard_backward_multi")
+                first = False
+                for v in range(V):
+                    stats.append((d2[v], radii[v]))
         # the background trajectory is shared by every Gaussian: its gradient sums over the shards
         if self.world > 1 and self.grads["background_deform"].numel():
             dist.all_reduce(self.grads["background_deform"], op=dist.ReduceOp.SUM, group=self.group)
-        for k in self.names:
-            getattr(m, k).grad = self.grads[k]
+        for name in self.names:
+            getattr(m, name).grad = self.grads[name]
         return results, stats

@@ -368,6 +368,20 @@ ADGS_API int adgs_shard_backward(const adgs_camera* cam, const adgs_model* model
                         const adgs_model* grads, int32_t accumulate, float* dL_dmeans2D, char* scratch,
                         adgs_stream_t stream);
 
+/* Multi-view variants (up to 8 views per call): ONE launch evaluates a shard for all views of a
+ * round -- parameters are read once, the backward sums the views in registers and writes every dense
+ * gradient once. Array arguments hold `num_views` entries. scratch: adgs_shard_scratch_bytes(). */
+#define ADGS_MAX_VIEWS 8
+ADGS_API size_t adgs_shard_scratch_bytes(int32_t num_views, int32_t N_obj);
+ADGS_API int adgs_shard_forward_multi(int32_t num_views, const adgs_camera* cams, const adgs_model* model,
+                             const adgs_time_basis* bases, int32_t render_objmask, const adgs_splats* outs,
+                             char* const* shard_states, adgs_stream_t stream);
+ADGS_API int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cams, const adgs_model* model,
+                              const adgs_time_basis* bases, const int32_t* const* radii,
+                              char* const* shard_states, const float* const* grad_records,
+                              const adgs_model* grads, int32_t accumulate, float* const* dL_dmeans2D,
+                              char* scratch, adgs_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): cumulative number of kernels launched by the library, and
  * optional CUDA-event timing of each pipeline stage on the caller's stream.

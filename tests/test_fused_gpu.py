@@ -210,6 +210,11 @@ def test_splat_exchange_step_matches_multi_view_step():
     ex.run(views, lambda v, r: cot, pipe)
     for k in want:
         assert Hh.rel_err(getattr(model, k).grad, want[k]) <= 1e-5, k
+    # all three views in ONE round: the multi-view kernels sum the views in registers
+    results, _ = ex.run(views, lambda v, r: cot, pipe, views_per_rank=3)
+    assert torch.equal(results[2]["render"], want_img)
+    for k in want:
+        assert Hh.rel_err(getattr(model, k).grad, want[k]) <= 1e-5, k
 
 
 def test_model_shards_partition_the_model():
