@@ -750,7 +750,7 @@ __global__ void __launch_bounds__(256, 2) shard_forward_multi_kernel(const __gri
     }
 }
 
-__global__ void __launch_bounds__(256, 1) shard_backward_multi_kernel(const __grid_constant__ MultiViewArgs a)
+__global__ void __launch_bounds__(128, 3) shard_backward_multi_kernel(const __grid_constant__ MultiViewArgs a)
 {
     __shared__ CamSmem cam;
     __shared__ float s_wshs[kMaxViews][ADGS_MAX_TERMS * 2];  // dense SH-deform weights per view and column
@@ -771,20 +771,11 @@ __global__ void __launch_bounds__(256, 1) shard_backward_multi_kernel(const __gr
     const int j = g - m.N_scene;
 
     float scale[3] = {1.f, 1.f, 1.f}, sig = 0.f;
-    float sh[48];
+    const float4* sh4 = reinterpret_cast<const float4*>(m.sh4);
     if (valid) {
 #pragma unroll
         for (int d = 0; d < 3; ++d) scale[d] = expf(m.scaling[3 * (size_t)g + d]);
         sig = 1.0f / (1.0f + expf(-m.opacity[g]));
-        const float4* sh4 = reinterpret_cast<const float4*>(m.sh4);
-#pragma unroll
-        for (int q = 0; q < 12; ++q) {
-            const float4 v = __ldg(sh4 + (size_t)q * N + g);
-            sh[4 * q + 0] = v.x;
-            sh[4 * q + 1] = v.y;
-            sh[4 * q + 2] = v.z;
-            sh[4 * q + 3] = v.w;
-        }
     }
     // accumulators over the views
     float axyz[3] = {0.f, 0.f, 0.f}, ascale[3] = {0.f, 0.f, 0.f}, adq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -833,17 +824,24 @@ __global__ void __launch_bounds__(256, 1) shard_backward_multi_kernel(const __gr
                 const float3 dm = cov2d_bwd(p, V.rp, cv, cam.view, g0.z, g0.w, g1.x, dcov);
                 const float3 dm2 = mean_proj_depth_bwd(p, cam.view, cam.proj, g0.x, g0.y, g2.y, V.rp.inv_depth);
                 const float4 sv2 = V.saved[(size_t)g * 3 + 2];
+                float sh[48];  // re-read per view: later views hit L1/L2, and no 48 registers stay live
+#pragma unroll
+                for (int q = 0; q < 12; ++q) {
+                    const float4 v = __ldg(sh4 + (size_t)q * N + g);
+                    sh[4 * q + 0] = v.x;
+                    sh[4 * q + 1] = v.y;
+                    sh[4 * q + 2] = v.z;
+                    sh[4 * q + 3] = v.w;
+                }
                 sh[0] = sv2.x;
                 sh[1] = sv2.y;
                 sh[2] = sv2.z;
                 const float dcol[3] = {g1.z, g1.w, g2.x};
-                float dsh[48];
-                const float3 dm3 = sh_to_rgb_bwd(V.rp.sh_degree, p, cam.campos, sh, V.clamped[g], dcol, dsh);
-#pragma unroll
-                for (int i = 0; i < 48; ++i) adsh[i] += dsh[i];
-                ddc[vi][0] = dsh[0];
-                ddc[vi][1] = dsh[1];
-                ddc[vi][2] = dsh[2];
+                const float before[3] = {adsh[0], adsh[1], adsh[2]};
+                const float3 dm3 = sh_to_rgb_bwd<true>(V.rp.sh_degree, p, cam.campos, sh, V.clamped[g], dcol, adsh);
+                ddc[vi][0] = adsh[0] - before[0];
+                ddc[vi][1] = adsh[1] - before[1];
+                ddc[vi][2] = adsh[2] - before[2];
                 dxt[0] = dm.x + dm2.x + dm3.x;
                 dxt[1] = dm.y + dm2.y + dm3.y;
                 dxt[2] = dm.z + dm2.z + dm3.z;
@@ -899,7 +897,7 @@ __global__ void __launch_bounds__(256, 1) shard_backward_multi_kernel(const __gr
             if (threadIdx.x < 6) {
                 float s = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += s_red[w][threadIdx.x];
                 if (s != 0.f) atomicAdd(V.bg_scratch + threadIdx.x, s);
             }
         }
@@ -1526,7 +1524,7 @@ int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cams, const 
     int st;
     {
         StageScope scope(kStagePerGaussianBwd, stream);
-        shard_backward_multi_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+        shard_backward_multi_kernel<<<(N + 127) / 128, 128, 0, stream>>>(a);
         count_launch(1);
     }
     if ((st = check_stage("shard backward (multi-view)", debug, stream))) return st;

@@ -278,6 +278,14 @@ __device__ __forceinline__ float3 normalize_vjp(const float3& v, const float3& d
 // Backward of sh_to_rgb (backward.cu:20-139): writes dL_dsh[0..3*M) (zeros above the active
 // degree) and returns the view-direction contribution to dL_dmean.
 // dsh: 48 floats out (coefficient-major). M: coefficients present (<=16).
+template <bool ACCUM>
+__device__ __forceinline__ void sh_put(float* dsh, int i, float v)
+{
+    if (ACCUM) dsh[i] += v; else dsh[i] = v;
+}
+
+// ACCUM = false: dsh is overwritten (zeros above the active degree); ACCUM = true: dsh += (multi-view sums).
+template <bool ACCUM = false>
 __device__ __forceinline__ float3 sh_to_rgb_bwd(int deg, const float3& pos, const float* campos, const float* sh,
                                                 uint32_t clamped_bits, const float* dL_dcolor, float* dsh)
 {
@@ -290,18 +298,20 @@ __device__ __forceinline__ float3 sh_to_rgb_bwd(int deg, const float3& pos, cons
     for (int c = 0; c < 3; ++c) g[c] = dL_dcolor[c] * ((clamped_bits >> c) & 1u ? 0.f : 1.f);
 
     float dx[3] = {0.f, 0.f, 0.f}, dy[3] = {0.f, 0.f, 0.f}, dz[3] = {0.f, 0.f, 0.f};
+    if (!ACCUM) {
 #pragma unroll
-    for (int i = 0; i < 48; ++i) dsh[i] = 0.f;
+        for (int i = 0; i < 48; ++i) dsh[i] = 0.f;
+    }
 
 #pragma unroll
-    for (int c = 0; c < 3; ++c) dsh[c] = ADGS_SH_C0 * g[c];
+    for (int c = 0; c < 3; ++c) sh_put<ACCUM>(dsh, c, ADGS_SH_C0 * g[c]);
     if (deg > 0) {
         const float b1 = -ADGS_SH_C1 * y, b2 = ADGS_SH_C1 * z, b3 = -ADGS_SH_C1 * x;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            dsh[3 + c] = b1 * g[c];
-            dsh[6 + c] = b2 * g[c];
-            dsh[9 + c] = b3 * g[c];
+            sh_put<ACCUM>(dsh, 3 + c, b1 * g[c]);
+            sh_put<ACCUM>(dsh, 6 + c, b2 * g[c]);
+            sh_put<ACCUM>(dsh, 9 + c, b3 * g[c]);
             dx[c] = -ADGS_SH_C1 * sh[9 + c];
             dy[c] = -ADGS_SH_C1 * sh[3 + c];
             dz[c] = ADGS_SH_C1 * sh[6 + c];
@@ -313,11 +323,11 @@ __device__ __forceinline__ float3 sh_to_rgb_bwd(int deg, const float3& pos, cons
                         b7 = ADGS_SH_C2_3 * xz, b8 = ADGS_SH_C2_4 * (xx - yy);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                dsh[12 + c] = b4 * g[c];
-                dsh[15 + c] = b5 * g[c];
-                dsh[18 + c] = b6 * g[c];
-                dsh[21 + c] = b7 * g[c];
-                dsh[24 + c] = b8 * g[c];
+                sh_put<ACCUM>(dsh, 12 + c, b4 * g[c]);
+                sh_put<ACCUM>(dsh, 15 + c, b5 * g[c]);
+                sh_put<ACCUM>(dsh, 18 + c, b6 * g[c]);
+                sh_put<ACCUM>(dsh, 21 + c, b7 * g[c]);
+                sh_put<ACCUM>(dsh, 24 + c, b8 * g[c]);
                 dx[c] += ADGS_SH_C2_0 * y * sh[12 + c] + ADGS_SH_C2_2 * 2.f * -x * sh[18 + c] +
                          ADGS_SH_C2_3 * z * sh[21 + c] + ADGS_SH_C2_4 * 2.f * x * sh[24 + c];
                 dy[c] += ADGS_SH_C2_0 * x * sh[12 + c] + ADGS_SH_C2_1 * z * sh[15 + c] +
@@ -333,13 +343,13 @@ __device__ __forceinline__ float3 sh_to_rgb_bwd(int deg, const float3& pos, cons
                             b15 = ADGS_SH_C3_6 * x * (xx - 3.f * yy);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    dsh[27 + c] = b9 * g[c];
-                    dsh[30 + c] = b10 * g[c];
-                    dsh[33 + c] = b11 * g[c];
-                    dsh[36 + c] = b12 * g[c];
-                    dsh[39 + c] = b13 * g[c];
-                    dsh[42 + c] = b14 * g[c];
-                    dsh[45 + c] = b15 * g[c];
+                    sh_put<ACCUM>(dsh, 27 + c, b9 * g[c]);
+                    sh_put<ACCUM>(dsh, 30 + c, b10 * g[c]);
+                    sh_put<ACCUM>(dsh, 33 + c, b11 * g[c]);
+                    sh_put<ACCUM>(dsh, 36 + c, b12 * g[c]);
+                    sh_put<ACCUM>(dsh, 39 + c, b13 * g[c]);
+                    sh_put<ACCUM>(dsh, 42 + c, b14 * g[c]);
+                    sh_put<ACCUM>(dsh, 45 + c, b15 * g[c]);
                     dx[c] += (ADGS_SH_C3_0 * sh[27 + c] * 3.f * 2.f * xy + ADGS_SH_C3_1 * sh[30 + c] * yz +
                               ADGS_SH_C3_2 * sh[33 + c] * -2.f * xy + ADGS_SH_C3_3 * sh[36 + c] * -3.f * 2.f * xz +
                               ADGS_SH_C3_4 * sh[39 + c] * (-3.f * xx + 4.f * zz - yy) +
