@@ -185,6 +185,8 @@ class Splats(C.Structure):
         ("depth_keys", C.c_void_p),
         ("tiles_touched", C.c_void_p),
         ("radii", C.c_void_p),
+        ("mean_x", C.c_void_p),
+        ("mean_y", C.c_void_p),
     ]
 
 
@@ -231,6 +233,10 @@ SIGNATURES = {
                                      C.c_void_p]),
     "adgs_splats_forward": (C.c_int, [_P(Camera), _P(Splats), C.c_int32, C.c_int32, _P(Images), C.c_void_p, C.c_void_p,
                                       C.c_int64, ALLOC_FN, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adgs_splats_bin": (C.c_int, [_P(Camera), _P(Splats), C.c_void_p, C.c_void_p, C.c_int64, ALLOC_FN, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
+    "adgs_splats_blend": (C.c_int, [_P(Camera), _P(Splats), C.c_int32, C.c_int32, _P(Images), C.c_void_p, C.c_void_p,
+                                    C.c_int64, C.c_void_p, C.c_void_p]),
     "adgs_splats_backward": (C.c_int, [_P(Camera), _P(Splats), C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,
                                        C.c_void_p, _P(ImageGrads), C.c_void_p, C.c_void_p]),
     "adgs_shard_backward": (C.c_int, [_P(Camera), _P(Model), _P(TimeBasis), C.c_void_p, C.c_void_p, C.c_void_p,

@@ -48,15 +48,17 @@ RasterParams make_raster_params(const adgs_camera* cam)
 int bin_and_blend(const adgs_camera* cam, int P, int D_S, bool has_flow, const float* semantic,
                   const adgs_images* out, const int32_t* radii, GeometryState& gs, char* binning,
                   adgs_alloc_fn binning_alloc, void* alloc_user, int64_t capacity, ImageState& is,
-                  bool sync_for_count, int* num_rendered, cudaStream_t stream)
+                  bool sync_for_count, int* num_rendered, cudaStream_t stream, int stages, const float* mean_x,
+                  const float* mean_y)
 {
     const bool debug = cam->debug != 0;
     const RasterParams rp = make_raster_params(cam);
     const int num_tiles = rp.grid_x * rp.grid_y;
     int st;
 
+    const bool do_bin = (stages & 1) != 0, do_blend = (stages & 2) != 0;
     // (1) Gaussians by (depth bits, id): 4 onesweep passes over 8 B/Gaussian.
-    {
+    if (do_bin) {
         StageScope sc(kStageDepthSort, stream);
         sort_pairs_async(gs.depth_keys, gs.depth_keys_alt, gs.order_a, gs.order_b, (size_t)P, nullptr, 0, 32, gs.sort,
                          /*iota*/ true, /*clear*/ true, stream);
@@ -64,14 +66,14 @@ int bin_and_blend(const adgs_camera* cam, int P, int D_S, bool has_flow, const f
     if ((st = check_stage("depth sort", debug, stream))) return st;
 
     // (2) offsets of every Gaussian's tile instances, in depth order; total -> counters[0]
-    {
+    if (do_bin) {
         StageScope sc(kStageScan, stream);
         inclusive_scan_gather_async(gs.tiles_touched, gs.depth_order, gs.point_offsets, (size_t)P, gs.scan_status,
                                     gs.counters, stream);
     }
     if ((st = check_stage("scan", debug, stream))) return st;
 
-    if (sync_for_count) {
+    if (sync_for_count && do_bin) {
         uint32_t R = 0;
         cudaError_t e = cudaMemcpyAsync(&R, gs.counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
@@ -83,15 +85,15 @@ int bin_and_blend(const adgs_camera* cam, int P, int D_S, bool has_flow, const f
     }
     BinningState bs = BinningState::from_chunk(binning, (size_t)capacity);
 
-    cudaMemsetAsync(is.ranges, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), stream);
-    const uint32_t* point_list = bs.vals_a;
-    if (capacity > 0) {
+    if (do_bin) cudaMemsetAsync(is.ranges, 0, (size_t)num_tiles * 2 * sizeof(uint32_t), stream);
+    const uint32_t* point_list = sorted_point_list(bs, num_tiles);
+    if (capacity > 0 && do_bin) {
         // (3) instances in depth order, (4) stable sort by tile id only
         {
             StageScope sc(kStageEmit, stream);
             launch_emit(P, gs.depth_order, gs.point_offsets, gs.tiles_touched,
                         reinterpret_cast<const float4*>(gs.record), radii, rp.grid_x, rp.grid_y, bs.keys_a, bs.vals_a,
-                        (uint32_t)capacity, gs.counters, stream);
+                        (uint32_t)capacity, gs.counters, stream, mean_x, mean_y);
         }
         if ((st = check_stage("emit", debug, stream))) return st;
         int passes;
@@ -108,6 +110,7 @@ int bin_and_blend(const adgs_camera* cam, int P, int D_S, bool has_flow, const f
         if ((st = check_stage("tile ranges", debug, stream))) return st;
     }
 
+    if (!do_blend) return ADGS_OK;
     BlendFwdArgs b;
     b.ranges = is.ranges;
     b.point_list = point_list;
@@ -209,7 +212,8 @@ static int forward_common(const adgs_camera* cam, const adgs_gaussians* g, const
     int st = check_stage("preprocess", cam->debug != 0, stream);
     if (st) return st;
     return bin_and_blend(cam, P, a.D_S, g->flow_points != nullptr, g->semantic, out, radii, gs, binning,
-                         binning_alloc, alloc_user, capacity, is, sync_for_count, num_rendered, stream);
+                         binning_alloc, alloc_user, capacity, is, sync_for_count, num_rendered, stream, 3, nullptr,
+                         nullptr);
 }
 
 }  // namespace adgs

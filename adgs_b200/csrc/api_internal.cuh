@@ -15,7 +15,8 @@ RasterParams make_raster_params(const adgs_camera* cam);
 int bin_and_blend(const adgs_camera* cam, int P, int D_S, bool has_flow, const float* semantic,
                   const adgs_images* out, const int32_t* radii, GeometryState& gs, char* binning,
                   adgs_alloc_fn binning_alloc, void* alloc_user, int64_t capacity, ImageState& is,
-                  bool sync_for_count, int* num_rendered, cudaStream_t stream);
+                  bool sync_for_count, int* num_rendered, cudaStream_t stream, int stages = 3,
+                  const float* mean_x = nullptr, const float* mean_y = nullptr);  // stages: 1 = bin, 2 = blend
 
 // ---- per-stage profiling / launch counting (profile.cu) ------------------------------------------
 enum Stage {

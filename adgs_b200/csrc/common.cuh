@@ -156,8 +156,8 @@ static inline void carve(char*& chunk, T*& ptr, size_t count, size_t alignment =
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 256;
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = 16;
-constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 pairs per CTA step
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 2048 pairs per CTA step
 constexpr int kMaxPasses = 4;
 
 struct SortWorkspace {

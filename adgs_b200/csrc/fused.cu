@@ -605,6 +605,8 @@ struct ViewIO {
     float* cov3D;
     uint8_t* clamped;
     float4* saved;
+    float* mean_x;             // optional planes of the pixel-space means (splat exchange)
+    float* mean_y;
     const float* grad_record;  // backward only
     float* dL_dmeans2D;        // backward only
     float4* dq_scratch;        // backward only
@@ -725,6 +727,10 @@ __global__ void __launch_bounds__(256, 2) shard_forward_multi_kernel(const __gri
             V.tiles_touched[g] = 0;
             V.depth_keys[g] = 0xFFFFFFFFu;
             continue;
+        }
+        if (V.mean_x) {
+            V.mean_x[g] = sg.px;
+            V.mean_y[g] = sg.py;
         }
         sh[0] = dc[0];
         sh[1] = dc[1];
@@ -1355,28 +1361,60 @@ int adgs_shard_forward(const adgs_camera* cam, const adgs_model* model, const ad
                                     stream);
 }
 
-int adgs_splats_forward(const adgs_camera* cam, const adgs_splats* splats, int32_t D_S, int32_t has_flow,
-                        const adgs_images* out, char* geometry, char* binning, int64_t capacity,
-                        adgs_alloc_fn binning_alloc, void* alloc_user, char* image, adgs_stream_t stream_)
+static int splats_forward_stages(const adgs_camera* cam, const adgs_splats* splats, int32_t D_S, int32_t has_flow,
+                                 const adgs_images* out, char* geometry, char* binning, int64_t capacity,
+                                 adgs_alloc_fn binning_alloc, void* alloc_user, char* image, cudaStream_t stream,
+                                 int stages)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
     int st = check_render_args(cam);
     if (st) return st;
-    if (!splats || !out || !geometry || !image || capacity < 0 || splats->P <= 0) return ADGS_ERR_ARG;
+    if (!splats || !geometry || !image || capacity < 0 || splats->P <= 0) return ADGS_ERR_ARG;
     if (!binning && !binning_alloc) return ADGS_ERR_ARG;
-    if (!out->depth || !out->opacity || D_S < 0 || D_S > 1) return ADGS_ERR_ARG;
+    if (D_S < 0 || D_S > 1) return ADGS_ERR_ARG;
+    if ((stages & 2) && (!out || !out->depth || !out->opacity || !splats->record)) return ADGS_ERR_ARG;
+    if ((stages & 1) && (!splats->depth_keys || !splats->tiles_touched || !splats->radii)) return ADGS_ERR_ARG;
+    if ((stages & 1) && !splats->record && !splats->mean_x) return ADGS_ERR_ARG;
     const int P = splats->P;
     GeometryState gs = GeometryState::from_chunk(geometry, (size_t)P);
     ImageState is = ImageState::from_chunk(image, cam->image_width, cam->image_height);
-    cudaMemsetAsync(gs.counters, 0, 32 * sizeof(uint32_t), stream);
+    if (stages & 1) cudaMemsetAsync(gs.counters, 0, 32 * sizeof(uint32_t), stream);
     // binning + blend read the per-Gaussian state from the caller's (gathered) arrays
     gs.record = splats->record;
     gs.depth_keys = splats->depth_keys;
     gs.tiles_touched = splats->tiles_touched;
     int R = 0;
-    st = bin_and_blend(cam, P, D_S, has_flow != 0, nullptr, out, splats->radii, gs, binning, binning_alloc, alloc_user,
-                       capacity, is, binning == nullptr, &R, stream);
+    adgs_images none;
+    memset(&none, 0, sizeof(none));
+    st = bin_and_blend(cam, P, D_S, has_flow != 0, nullptr, out ? out : &none, splats->radii, gs, binning,
+                       binning_alloc, alloc_user, capacity, is, binning == nullptr, &R, stream, stages,
+                       splats->mean_x, splats->mean_y);
     return st ? st : R;
+}
+
+int adgs_splats_forward(const adgs_camera* cam, const adgs_splats* splats, int32_t D_S, int32_t has_flow,
+                        const adgs_images* out, char* geometry, char* binning, int64_t capacity,
+                        adgs_alloc_fn binning_alloc, void* alloc_user, char* image, adgs_stream_t stream_)
+{
+    return splats_forward_stages(cam, splats, D_S, has_flow, out, geometry, binning, capacity, binning_alloc,
+                                 alloc_user, image, (cudaStream_t)stream_, 3);
+}
+
+int adgs_splats_bin(const adgs_camera* cam, const adgs_splats* splats, char* geometry, char* binning,
+                    int64_t capacity, adgs_alloc_fn binning_alloc, void* alloc_user, char* image,
+                    adgs_stream_t stream_)
+{
+    return splats_forward_stages(cam, splats, 0, 0, nullptr, geometry, binning, capacity, binning_alloc, alloc_user,
+                                 image, (cudaStream_t)stream_, 1);
+}
+
+int adgs_splats_blend(const adgs_camera* cam, const adgs_splats* splats, int32_t D_S, int32_t has_flow,
+                      const adgs_images* out, char* geometry, char* binning, int64_t capacity, char* image,
+                      adgs_stream_t stream_)
+{
+    if (!binning) return ADGS_ERR_ARG;
+    int st = splats_forward_stages(cam, splats, D_S, has_flow, out, geometry, binning, capacity, nullptr, nullptr,
+                                   image, (cudaStream_t)stream_, 2);
+    return st < 0 ? st : ADGS_OK;
 }
 
 int adgs_splats_backward(const adgs_camera* cam, const adgs_splats* splats, int32_t D_S, int32_t has_flow,
@@ -1456,6 +1494,8 @@ int adgs_shard_forward_multi(int32_t num_views, const adgs_camera* cams, const a
         V.cov3D = ss.cov3D;
         V.clamped = ss.clamped;
         V.saved = ss.saved;
+        V.mean_x = outs[v].mean_x;
+        V.mean_y = outs[v].mean_y;
     }
     {
         StageScope sc(kStagePerGaussianFwd, stream);

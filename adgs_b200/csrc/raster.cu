@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(256) emit_kernel(int P, const uint32_t* __rest
                                                    const float4* __restrict__ record,
                                                    const int32_t* __restrict__ radii, int grid_x, int grid_y,
                                                    uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                   uint32_t capacity, uint32_t* counters)
+                                                   uint32_t capacity, uint32_t* counters,
+                                                   const float* __restrict__ mean_x, const float* __restrict__ mean_y)
 {
     constexpr uint32_t kCoop = 32;  // splats with more tiles than this are emitted cooperatively
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,8 +146,16 @@ __global__ void __launch_bounds__(256) emit_kernel(int P, const uint32_t* __rest
                 counters[1] = 1;  // overflow: binning arena too small
                 n = 0;
             } else {
-                const float4 q0 = record[(size_t)gid * 4];
-                tile_rect(q0.x, q0.y, radii[gid], grid_x, grid_y, x0, y0, x1, y1);
+                float mx, my;
+                if (mean_x) {  // splat exchange: the pixel means travel apart from the (larger) records
+                    mx = mean_x[gid];
+                    my = mean_y[gid];
+                } else {
+                    const float4 q0 = record[(size_t)gid * 4];
+                    mx = q0.x;
+                    my = q0.y;
+                }
+                tile_rect(mx, my, radii[gid], grid_x, grid_y, x0, y0, x1, y1);
             }
         }
     }
@@ -329,12 +338,12 @@ void launch_mark_visible(int P, const float* means3D, const float* view, const f
 
 void launch_emit(int P, const uint32_t* depth_order, const uint32_t* point_offsets, const uint32_t* tiles_touched,
                  const float4* record, const int32_t* radii, int grid_x, int grid_y, uint32_t* keys, uint32_t* vals,
-                 uint32_t capacity, uint32_t* counters, cudaStream_t stream)
+                 uint32_t capacity, uint32_t* counters, cudaStream_t stream, const float* mean_x, const float* mean_y)
 {
     if (P <= 0) return;
     count_launch(1);
     emit_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, depth_order, point_offsets, tiles_touched, record, radii,
-                                                     grid_x, grid_y, keys, vals, capacity, counters);
+                                                     grid_x, grid_y, keys, vals, capacity, counters, mean_x, mean_y);
 }
 
 void launch_tile_ranges(const uint32_t* sorted_tiles, const uint32_t* counters, uint32_t capacity, uint32_t* ranges,

@@ -66,7 +66,8 @@ void launch_mark_visible(int P, const float* means3D, const float* view, const f
 // reference's 64-bit key sort (rasterizer_impl.cu:70-111, 310-315) at a fraction of the traffic.
 void launch_emit(int P, const uint32_t* depth_order, const uint32_t* point_offsets, const uint32_t* tiles_touched,
                  const float4* record, const int32_t* radii, int grid_x, int grid_y, uint32_t* keys,
-                 uint32_t* vals, uint32_t capacity, uint32_t* counters, cudaStream_t stream);
+                 uint32_t* vals, uint32_t capacity, uint32_t* counters, cudaStream_t stream,
+                 const float* mean_x = nullptr, const float* mean_y = nullptr);
 void launch_tile_ranges(const uint32_t* sorted_tiles, const uint32_t* counters, uint32_t capacity,
                         uint32_t* ranges, cudaStream_t stream);
 

@@ -309,7 +309,7 @@ int sort_pairs_async(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint3
     uint32_t* kout = keys_b;
     uint32_t* vin = vals_a;
     uint32_t* vout = vals_b;
-    const int grid = (int)min((size_t)sms * 2, tiles);
+    const int grid = (int)min((size_t)sms * 4, tiles);
     for (int p = 0; p < passes; ++p) {
         const int shift = begin_bit + p * kRadixBits;
         const int bits = min(kRadixBits, end_bit - shift);

@@ -219,26 +219,38 @@ class SplatExchangeStep:
             with torch.cuda.device(dev):
                 # ---- front end of my shard for every view of the round: ONE launch ---------------------
                 rec = torch.empty((V, n, 16), **o)
-                keys = torch.empty((V, n), dtype=torch.int32, device=dev)
-                tiles = torch.empty((V, n), dtype=torch.int32, device=dev)
-                radii = torch.empty((V, n), dtype=torch.int32, device=dev)
+                # small per-splat state in one buffer: planes 0 depth key, 1 tiles touched, 2 radius,
+                # 3 pixel mean x, 4 pixel mean y (20 B per splat: all that binning needs)
+                meta = torch.empty((V, 5, n), dtype=torch.int32, device=dev)
                 state = torch.empty((V, lib.adgs_shard_state_bytes(n)), dtype=torch.uint8, device=dev)
                 cams = [self._camera(cam, pipe, keep) for cam, _ in batch]
                 bases = [m.time_basis(cam.time, flow_t) for cam, flow_t in batch]
                 cam_arr = (L.Camera * V)(*cams)
                 basis_arr = (L.TimeBasis * V)(*bases)
                 splat_arr = (L.Splats * V)(*[L.Splats(P=n, _pad=0, record=rec[v].data_ptr(),
-                                                      depth_keys=keys[v].data_ptr(), tiles_touched=tiles[v].data_ptr(),
-                                                      radii=radii[v].data_ptr()) for v in range(V)])
+                                                      depth_keys=meta[v, 0].data_ptr(),
+                                                      tiles_touched=meta[v, 1].data_ptr(), radii=meta[v, 2].data_ptr(),
+                                                      mean_x=meta[v, 3].data_ptr(), mean_y=meta[v, 4].data_ptr())
+                                             for v in range(V)])
                 state_arr = (C.c_void_p * V)(*[state[v].data_ptr() for v in range(V)])
                 cmodel = m.c_model()
                 L.check(lib.adgs_shard_forward_multi(V, cam_arr, C.byref(cmodel), basis_arr, int(self.render_objmask),
                                                      splat_arr, state_arr, stream), "shard_forward_multi")
-                # ---- splats of view v travel to the rank that blends it (chunk d of dim 0 -> rank d) ------
-                r_rec = self._all_to_all(rec).view(G, k, n, 16)
-                r_keys = self._all_to_all(keys).view(G, k, n)
-                r_tiles = self._all_to_all(tiles).view(G, k, n)
-                r_radii = self._all_to_all(radii).view(G, k, n)
+                radii = meta[:, 2]
+                # ---- splats travel to the rank that blends their view (chunk d of dim 0 -> rank d): the
+                #      20-byte binning state first, the 64-byte records behind it on the NCCL stream, so
+                #      that sorting and binning overlap the bulk of the transfer ---------------------------
+                if G > 1:
+                    r_meta = torch.empty_like(meta)
+                    r_rec = torch.empty_like(rec)
+                    w_meta = dist.all_to_all_single(r_meta, meta, group=self.group, async_op=True)
+                    w_rec = dist.all_to_all_single(r_rec, rec, group=self.group, async_op=True)
+                    w_meta.wait()
+                else:
+                    r_meta, r_rec, w_rec = meta, rec, None
+                # (G, k, 5, n) -> per local view and plane, rank-major over the shards
+                r_meta = r_meta.view(G, k, 5, n).permute(1, 2, 0, 3).contiguous()      # (k, 5, G, n)
+                r_rec = r_rec.view(G, k, n, 16)
                 gback = torch.empty((G, k, n, 16), **o)
                 P = G * n
                 for i in range(k):
@@ -246,21 +258,18 @@ class SplatExchangeStep:
                     cam, flow_t = batch[v_glob]
                     cc = cams[v_glob]
                     H, W = int(cam.image_height), int(cam.image_width)
-                    # all shards of my i-th view, rank-major (a plain view when k == 1)
-                    s_rec = r_rec[:, i].reshape(P, 16)
-                    s_keys = r_keys[:, i].reshape(P)
-                    if s_keys.data_ptr() == keys.data_ptr():
-                        s_keys = s_keys.clone()          # G == k == 1: keep the front end's keys intact
-                    s_tiles = r_tiles[:, i].reshape(P)
-                    s_radii = r_radii[:, i].reshape(P)
+                    # all shards of my i-th view, rank-major
+                    s_keys, s_tiles, s_radii = r_meta[i, 0].view(-1), r_meta[i, 1].view(-1), r_meta[i, 2].view(-1)
+                    s_mx, s_my = r_meta[i, 3].view(-1), r_meta[i, 4].view(-1)
                     img = dict(color=torch.empty((3, H, W), **o), depth=torch.empty((1, H, W), **o),
                                opacity=torch.empty((1, H, W), **o), flow=torch.empty((3, H, W), **o),
                                semantic=torch.empty((D_S, H, W), **o))
                     images = L.Images(color=L.ptr(img["color"]), depth=L.ptr(img["depth"]),
                                       opacity=L.ptr(img["opacity"]), flow=L.ptr(img["flow"]),
                                       semantic=L.ptr(img["semantic"]), radii=None)
-                    splats = L.Splats(P=P, _pad=0, record=s_rec.data_ptr(), depth_keys=s_keys.data_ptr(),
-                                      tiles_touched=s_tiles.data_ptr(), radii=s_radii.data_ptr())
+                    splats = L.Splats(P=P, _pad=0, record=None, depth_keys=s_keys.data_ptr(),
+                                      tiles_touched=s_tiles.data_ptr(), radii=s_radii.data_ptr(),
+                                      mean_x=s_mx.data_ptr(), mean_y=s_my.data_ptr())
                     geom = torch.empty((lib.adgs_geometry_bytes(P),), dtype=torch.uint8, device=dev)
                     imgbuf = torch.empty((lib.adgs_image_bytes(W, H),), dtype=torch.uint8, device=dev)
                     has_flow = int(flow_t is not None)
@@ -268,9 +277,8 @@ class SplatExchangeStep:
                     if sync_free:
                         capacity = self._capacity
                         binning = torch.empty((lib.adgs_binning_bytes(capacity),), dtype=torch.uint8, device=dev)
-                        L.check(lib.adgs_splats_forward(C.byref(cc), C.byref(splats), D_S, has_flow, C.byref(images),
-                                                        L.ptr(geom), L.ptr(binning), capacity, L.ALLOC_FN(), None,
-                                                        L.ptr(imgbuf), stream), "splats_forward")
+                        L.check(lib.adgs_splats_bin(C.byref(cc), C.byref(splats), L.ptr(geom), L.ptr(binning), capacity,
+                                                    L.ALLOC_FN(), None, L.ptr(imgbuf), stream), "splats_bin")
                         counters = m._pinned_counters()
                         L.check(lib.adgs_read_counters(L.ptr(geom), P, counters.data_ptr(), stream), "read_counters")
                         ev = torch.cuda.Event()
@@ -283,12 +291,20 @@ class SplatExchangeStep:
                             return holder["b"].data_ptr()
 
                         cb = L.ALLOC_FN(_alloc)
-                        R = L.check(lib.adgs_splats_forward(C.byref(cc), C.byref(splats), D_S, has_flow,
-                                                            C.byref(images), L.ptr(geom), None, 0, cb, None,
-                                                            L.ptr(imgbuf), stream), "splats_forward")
+                        R = L.check(lib.adgs_splats_bin(C.byref(cc), C.byref(splats), L.ptr(geom), None, 0, cb, None,
+                                                        L.ptr(imgbuf), stream), "splats_bin")
                         binning, capacity = holder["b"], int(R)
                         self._capacity = max(self._capacity, int(1.3 * R) + 65536)
                         counters = ev = None
+                    # ---- the records have (by now, mostly) arrived: blend ---------------------------------
+                    if w_rec is not None:
+                        w_rec.wait()
+                        w_rec = None
+                    s_rec = r_rec[:, i].reshape(P, 16)          # a plain view when k == 1
+                    splats.record = s_rec.data_ptr()
+                    L.check(lib.adgs_splats_blend(C.byref(cc), C.byref(splats), D_S, has_flow, C.byref(images),
+                                                  L.ptr(geom), L.ptr(binning), int(capacity), L.ptr(imgbuf), stream),
+                            "splats_blend")
                     res = {"render": img["color"], "depth": img["depth"][0], "img_opacity": img["opacity"][0],
                            "img_flow": img["flow"] if has_flow else None,
                            "img_semantic": img["semantic"] if self.render_objmask else None, "radii": s_radii}
@@ -314,6 +330,7 @@ class SplatExchangeStep:
                         gback[:, i] = grec.view(G, n, 16)
                 # ---- gradient records back to the owners; per-Gaussian backward of my shard: ONE launch ----
                 r_grec = self._all_to_all(gback.view(V, n, 16))
+                del r_meta
                 scratch = torch.empty((lib.adgs_shard_scratch_bytes(V, m.n_obj),), dtype=torch.uint8, device=dev)
                 gm = m.c_model_from(self.grads, with_time=False)
                 d2 = torch.empty((V, n, 3), **o)

@@ -352,6 +352,8 @@ typedef struct adgs_splats {
     uint32_t* depth_keys;    /* (P) float bits of view-space z, ~0 if culled; clobbered by the sort */
     uint32_t* tiles_touched; /* (P) */
     int32_t* radii;          /* (P) */
+    float* mean_x;           /* (P) optional: pixel-space means as separate planes, so that binning can */
+    float* mean_y;           /* (P)           start before the (4x larger) records have arrived         */
 } adgs_splats;
 
 ADGS_API size_t adgs_shard_state_bytes(int32_t N);
@@ -360,6 +362,15 @@ ADGS_API int adgs_shard_forward(const adgs_camera* cam, const adgs_model* model,
 ADGS_API int adgs_splats_forward(const adgs_camera* cam, const adgs_splats* splats, int32_t D_S, int32_t has_flow,
                         const adgs_images* out, char* geometry, char* binning, int64_t capacity,
                         adgs_alloc_fn binning_alloc, void* alloc_user, char* image, adgs_stream_t stream);
+/* adgs_splats_forward split in two, so that the all-to-all of the records overlaps the binning:
+ * adgs_splats_bin needs depth_keys / tiles_touched / radii / mean_x / mean_y only; adgs_splats_blend
+ * needs the records and the arenas adgs_splats_bin filled. */
+ADGS_API int adgs_splats_bin(const adgs_camera* cam, const adgs_splats* splats, char* geometry, char* binning,
+                    int64_t capacity, adgs_alloc_fn binning_alloc, void* alloc_user, char* image,
+                    adgs_stream_t stream);
+ADGS_API int adgs_splats_blend(const adgs_camera* cam, const adgs_splats* splats, int32_t D_S, int32_t has_flow,
+                      const adgs_images* out, char* geometry, char* binning, int64_t capacity, char* image,
+                      adgs_stream_t stream);
 ADGS_API int adgs_splats_backward(const adgs_camera* cam, const adgs_splats* splats, int32_t D_S, int32_t has_flow,
                          const char* binning, int64_t capacity, const char* image, const float* img_opacity,
                          const adgs_image_grads* dpix, float* grad_record, adgs_stream_t stream);
