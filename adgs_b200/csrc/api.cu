@@ -419,6 +419,7 @@ int adgs_rasterize_backward(const adgs_camera* cam, const adgs_gaussians* g, con
     b.dL_dopacity = dpix->dL_dopacity;
     b.grad_record = grad_record;
     b.dL_dsemantic_g = grads->dL_dsemantic;
+    b.counters = nullptr;  // exact binning: the arena was sized from num_rendered
     if (D_S > 1 && !grads->dL_dsemantic) return ADGS_ERR_ARG;
     if (R > 0) {
         {

@@ -37,6 +37,8 @@ struct BlendBwdArgs {
     const float* dL_dopacity;
     float* grad_record;    // [P][16] zero-initialised accumulation target
     float* dL_dsemantic_g; // (P,D_S) for D_S > 1 (zero-initialised)
+    const uint32_t* counters;  // [1] = binning overflow of the forward (sync-free mode): leave the
+                               // gradient record zero instead of reading images that were never written
 };
 
 // Conservative test: can ANY pixel centre of the rectangle [X0,X1]x[Y0,Y1] receive

@@ -1086,7 +1086,7 @@ int run_per_gaussian_forward(const adgs_camera* cam, const adgs_model* model, co
 
 int run_blend_backward(const adgs_camera* cam, int P, int render_objmask, bool has_flow, const float4* record,
                        const BinningState& bs, const ImageState& is, int64_t capacity, const float* img_opacity,
-                       const adgs_image_grads* dpix, float* grad_record, cudaStream_t stream)
+                       const adgs_image_grads* dpix, float* grad_record, const uint32_t* counters, cudaStream_t stream)
 {
     const RasterParams rp = make_raster_params(cam);
     {
@@ -1112,6 +1112,7 @@ int run_blend_backward(const adgs_camera* cam, int P, int render_objmask, bool h
     b.dL_dopacity = dpix->dL_dopacity;
     b.grad_record = grad_record;
     b.dL_dsemantic_g = nullptr;
+    b.counters = counters;
     if (capacity > 0) {
         StageScope sc(kStageBlendBwd, stream);
         launch_blend_backward(b, has_flow, stream);
@@ -1315,7 +1316,7 @@ int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const 
     carve(svc, saved4, (size_t)N * 3);
     if ((st = run_blend_backward(cam, N, render_objmask, basis->has_flow != 0,
                                  reinterpret_cast<const float4*>(gs.record), bs, is, capacity, img_opacity, dpix,
-                                 grad_record, stream)))
+                                 grad_record, gs.counters, stream)))
         return st;
     return run_per_gaussian_backward(cam, model, basis, radii, gs.cov3D, gs.clamped, saved4, grad_record, grads, 0,
                                      dL_dmeans2D, dq_scratch, bg_scratch, stream);
@@ -1431,7 +1432,7 @@ int adgs_splats_backward(const adgs_camera* cam, const adgs_splats* splats, int3
     BinningState bs = BinningState::from_chunk(bc, (size_t)capacity);
     ImageState is = ImageState::from_chunk(ic, cam->image_width, cam->image_height);
     return run_blend_backward(cam, splats->P, D_S, has_flow != 0, reinterpret_cast<const float4*>(splats->record), bs,
-                              is, capacity, img_opacity, dpix, grad_record, stream);
+                              is, capacity, img_opacity, dpix, grad_record, nullptr, stream);
 }
 
 int adgs_shard_backward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,

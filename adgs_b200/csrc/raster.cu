@@ -190,6 +190,9 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __rest
                                                           const uint32_t* __restrict__ counters, uint32_t capacity,
                                                           uint32_t* __restrict__ ranges)
 {
+    // overflow (sync-free mode): the tail of the list was never emitted and holds arbitrary tile ids;
+    // the blend kernels skip such a frame, so no range is needed -- and none may be derived from garbage
+    if (counters[1]) return;
     const uint32_t L = min(counters[0], capacity);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < L; idx += stride) {

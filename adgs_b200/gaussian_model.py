@@ -323,6 +323,31 @@ class GaussianModel(nn.Module):
         self._last_num_rendered = int(R)
         self._binning_capacity = max(self._binning_capacity, int(1.3 * R) + 65536)
 
+    def _defer_counter_check(self, counters, event, capacity):
+        self.__dict__.setdefault("_counter_checks", []).append((counters, event, int(capacity)))
+
+    def _resolve_counter_checks(self, block: bool):
+        """Look at the {num_rendered, overflow} words of earlier sync-free forwards: grow the binning arena,
+        and report a dropped iteration (the device already zeroed its gradients). block=False only takes the
+        ones whose copy has landed."""
+        checks = self.__dict__.get("_counter_checks")
+        if not checks:
+            return
+        rest = []
+        for counters, event, capacity in checks:
+            if not block and not event.query():
+                rest.append((counters, event, capacity))
+                continue
+            event.synchronize()
+            R, ovf = int(counters[0]), bool(counters[1])
+            self._note_num_rendered(R)
+            if ovf or R > capacity:
+                import warnings
+                warnings.warn("adgs_b200: the binning arena overflowed in a sync-free forward; that iteration's "
+                              "images are invalid and its gradients were zeroed on the device; the arena has been "
+                              "enlarged (see DESIGN.md, 'sync-free binning')")
+        self.__dict__["_counter_checks"] = rest
+
     def time_basis(self, t, flow_t=None) -> L.TimeBasis:
         """Host-side basis for (t, flow_t); cached -- a training run revisits the same frame times."""
         key = (float(t), None if flow_t is None else float(flow_t), bool(self.use_time_mask))

@@ -10,8 +10,6 @@ DESIGN.md: the deformed tensors (`xyz`, `rotation`, `shs`) are only materialised
 import ctypes as C
 import math
 import threading
-import warnings
-
 import torch
 
 from . import _lib as L
@@ -40,6 +38,7 @@ class _FusedRender(torch.autograd.Function):
                 materialize):
         lib = L.load()
         dev = xyz.device
+        model._resolve_counter_checks(block=True)   # arena size for this forward (previous step's counters)
         N, H, W = model.get_pts_num, int(settings.image_height), int(settings.image_width)
         o = dict(dtype=torch.float32, device=dev)
         color = torch.empty((3, H, W), **o)
@@ -120,35 +119,29 @@ class _FusedRender(torch.autograd.Function):
         sink = getattr(model, "_grad_sink", None)
         grads = sink() if sink is not None else {k: torch.empty_like(v) for k, v in tensors.items()}
         d_means2D = torch.empty((N, 3), dtype=torch.float32, device=dev)
-        overflow = False
+        # Sync-free forward: {num_rendered, overflow} is on its way to pinned memory. The backward does not
+        # wait for it -- the blend backward reads the overflow flag on the device and leaves every gradient
+        # zero if the arena was too small -- so the host never blocks inside a step; the counters are looked
+        # at when they have arrived (here, if the forward is already done, else before the next forward).
         if ctx.pending is not None:
-            counters, ev = ctx.pending
-            ev.synchronize()
-            model._note_num_rendered(int(counters[0]))
-            overflow = bool(counters[1]) or int(counters[0]) > ctx.capacity
-        if overflow:
-            warnings.warn("adgs_b200: binning arena overflowed in a sync-free forward; this iteration's gradients "
-                          "are zeroed and the arena has been enlarged (see DESIGN.md, 'sync-free binning')")
-            for v in grads.values():
-                v.zero_()
-            d_means2D.zero_()
-        else:
-            keep = []
-            with torch.cuda.device(dev):
-                cam = _camera(settings, keep)
-                cm = model.c_model_from(tensors)
-                gm = model.c_model_from(grads, with_time=False)
-                cot = [None if g is None else g.contiguous() for g in (g_color, g_depth, g_flow, g_sem, g_opacity)]
-                ig = L.ImageGrads(dL_dcolor=L.ptr(cot[0]), dL_ddepth=L.ptr(cot[1]), dL_dflow=L.ptr(cot[2]),
-                                  dL_dsemantic=L.ptr(cot[3]) if ctx.render_objmask else None,
-                                  dL_dopacity=L.ptr(cot[4]))
-                scratch = torch.empty((lib.adgs_render_scratch_bytes(N, model.n_obj),), dtype=torch.uint8, device=dev)
-                st = lib.adgs_render_backward(C.byref(cam), C.byref(cm), C.byref(tb), int(ctx.render_objmask),
-                                              L.ptr(radii), L.ptr(geom), L.ptr(binning), int(ctx.capacity), L.ptr(img),
-                                              L.ptr(saved), L.ptr(img_opacity), C.byref(ig), C.byref(gm),
-                                              L.ptr(d_means2D), L.ptr(scratch),
-                                              torch.cuda.current_stream(dev).cuda_stream)
-                L.check(st, "render_backward")
+            model._defer_counter_check(ctx.pending[0], ctx.pending[1], ctx.capacity)
+            model._resolve_counter_checks(block=False)
+        keep = []
+        with torch.cuda.device(dev):
+            cam = _camera(settings, keep)
+            cm = model.c_model_from(tensors)
+            gm = model.c_model_from(grads, with_time=False)
+            cot = [None if g is None else g.contiguous() for g in (g_color, g_depth, g_flow, g_sem, g_opacity)]
+            ig = L.ImageGrads(dL_dcolor=L.ptr(cot[0]), dL_ddepth=L.ptr(cot[1]), dL_dflow=L.ptr(cot[2]),
+                              dL_dsemantic=L.ptr(cot[3]) if ctx.render_objmask else None,
+                              dL_dopacity=L.ptr(cot[4]))
+            scratch = torch.empty((lib.adgs_render_scratch_bytes(N, model.n_obj),), dtype=torch.uint8, device=dev)
+            st = lib.adgs_render_backward(C.byref(cam), C.byref(cm), C.byref(tb), int(ctx.render_objmask),
+                                          L.ptr(radii), L.ptr(geom), L.ptr(binning), int(ctx.capacity), L.ptr(img),
+                                          L.ptr(saved), L.ptr(img_opacity), C.byref(ig), C.byref(gm),
+                                          L.ptr(d_means2D), L.ptr(scratch),
+                                          torch.cuda.current_stream(dev).cuda_stream)
+            L.check(st, "render_backward")
         return (d_means2D,) + tuple(grads[k] for k in PARAM_NAMES) + (None,) * 7
 
 

@@ -125,6 +125,41 @@ def test_sync_free_path_equals_sync_path():
             assert Hh.rel_err(a, b) <= 1e-5
 
 
+def test_sync_free_overflow_zeroes_gradients_on_device_and_recovers():
+    """A sync-free forward whose binning arena is too small must not produce wrong gradients: the blend
+    backward sees the overflow flag on the device and leaves every gradient zero, the host learns about it
+    before the next forward (warning + larger arena), and that next iteration is correct again."""
+    import warnings
+    order_args, ref, c = _scene(4000, 1000, "kitti75")
+    model = GaussianModel.from_reference({f: getattr(ref, f) for f in ref.FIELDS}, order_args)
+    cam = c["cam"]
+    vcam = SimpleNamespace(image_height=c["H"], image_width=c["W"], FoVx=cam.FoVx, FoVy=cam.FoVy,
+                           world_view_transform=cam.world_view_transform, full_proj_transform=cam.full_proj_transform,
+                           camera_center=cam.camera_center, time=0.6)
+    cot = Hh.cotangents(c)
+    pipe = SimpleNamespace(inv_depth=True, debug=False, sync_free=True)
+
+    def step():
+        model.zero_grad()
+        res = render(vcam, model, None, pipe, flow_pkg=[0.7, None, None, None, None, None], render_objmask=True)
+        ((res["render"] * cot["color"]).sum() + (res["depth"] * cot["depth"][0]).sum()).backward()
+        return model.xyz.grad.clone(), model.sh4.grad.clone()
+
+    good = step()                      # first call: exact (synchronising) path, sizes the arena
+    assert good[0].abs().max() > 0
+    model._binning_capacity = 64       # far too small for the next sync-free forward
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        bad = step()
+        torch.cuda.synchronize()
+        assert bad[0].abs().max() == 0 and bad[1].abs().max() == 0, "gradients of an overflowed iteration must be 0"
+        again = step()                 # by now the counters have been looked at: warned, enlarged, correct again
+    assert any("overflow" in str(x.message) for x in w)
+    assert model._binning_capacity > 64
+    for a, b in zip(again, good):
+        assert Hh.rel_err(a, b) <= 1e-5
+
+
 def test_trajectory_only_matches_oracle():
     from oracle import trajectory_oracle as TO
     for key in ORDER_SETS:
