@@ -35,6 +35,7 @@ enum Stage {
 };
 
 void count_launch(int n);
+int tune_variant(const char* env_name, int dflt);  // integer tuning knob from the environment (profile.cu)
 
 struct StageScope {
     StageScope(int stage, cudaStream_t stream);

@@ -99,7 +99,8 @@ __device__ __forceinline__ float4 object_rotation_raw(const adgs_model& m, const
     return q;
 }
 
-__global__ void __launch_bounds__(256, 3) fused_forward_kernel(const __grid_constant__ FusedFwdArgs a)
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) fused_forward_kernel(const __grid_constant__ FusedFwdArgs a)
 {
     __shared__ CamSmem cam;
     __shared__ float s_bg[6];
@@ -310,11 +311,12 @@ __device__ __forceinline__ void put4(float4* p, float4 v, int acc)
     *p = v;
 }
 
-__global__ void __launch_bounds__(256, 2) fused_backward_kernel(const __grid_constant__ FusedBwdArgs a)
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_constant__ FusedBwdArgs a)
 {
     __shared__ CamSmem cam;
     __shared__ float s_wshs[ADGS_MAX_TERMS * 2];  // dense SH-deform weights per column
-    __shared__ float s_red[8][6];
+    __shared__ float s_red[TPB / 32][6];
     const adgs_model& m = a.m;
     const adgs_time_basis& tb = a.tb;
     const int N = m.N_scene + m.N_obj;
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(256, 2) fused_backward_kernel(const __grid_con
         if (threadIdx.x < 6) {
             float s = 0.f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
+            for (int w = 0; w < TPB / 32; ++w) s += s_red[w][threadIdx.x];
             if (s != 0.f) atomicAdd(a.bg_scratch + threadIdx.x, s);
         }
     }
@@ -1046,6 +1048,30 @@ __global__ void background_finalize_multi_kernel(const __grid_constant__ MultiVi
 
 // ---- host-side stages shared by the single-GPU entry points and the splat-exchange entry points ----
 
+void launch_fused_forward(const FusedFwdArgs& a, int N, cudaStream_t stream)
+{
+    // measured on B200 (profiles/README.md, sweep r1d): 128 threads x 8 CTAs/SM (64 registers) 0.135 ms,
+    // 256 x 3 (80 registers) 0.153 ms -- latency-bound on HBM, so occupancy beats the few spilled words
+    static const int v = tune_variant("ADGS_TUNE_FWD", 0);
+    switch (v) {
+    case 1: fused_forward_kernel<256, 3><<<(N + 255) / 256, 256, 0, stream>>>(a); break;
+    case 2: fused_forward_kernel<256, 4><<<(N + 255) / 256, 256, 0, stream>>>(a); break;
+    default: fused_forward_kernel<128, 8><<<(N + 127) / 128, 128, 0, stream>>>(a); break;
+    }
+    count_launch(1);
+}
+
+void launch_fused_backward(const FusedBwdArgs& a, int N, cudaStream_t stream)
+{
+    // sweep r1d: 128 x 4 (128 registers) 0.220 ms, 256 x 2 0.229 ms; 96 / 80 registers spill and lose (0.26 / 0.32 ms)
+    static const int v = tune_variant("ADGS_TUNE_PGB", 0);
+    switch (v) {
+    case 1: fused_backward_kernel<256, 2><<<(N + 255) / 256, 256, 0, stream>>>(a); break;
+    default: fused_backward_kernel<128, 4><<<(N + 127) / 128, 128, 0, stream>>>(a); break;
+    }
+    count_launch(1);
+}
+
 struct SplatPtrs {  // per-Gaussian per-view state consumed by binning + blend
     float4* record;
     uint32_t* depth_keys;
@@ -1078,8 +1104,7 @@ int run_per_gaussian_forward(const adgs_camera* cam, const adgs_model* model, co
     a.saved = saved;
     {
         StageScope sc(kStagePerGaussianFwd, stream);
-        fused_forward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
-        count_launch(1);
+        launch_fused_forward(a, N, stream);
     }
     return check_stage("fused forward", cam->debug != 0, stream);
 }
@@ -1188,8 +1213,7 @@ int run_per_gaussian_backward(const adgs_camera* cam, const adgs_model* model, c
     a.accumulate = accumulate;
     {
         StageScope sc(kStagePerGaussianBwd, stream);
-        fused_backward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
-        count_launch(1);
+        launch_fused_backward(a, N, stream);
     }
     if ((st = check_stage("fused backward", debug, stream))) return st;
     if (No > 0) {
@@ -1228,8 +1252,7 @@ int adgs_trajectory_forward(const adgs_model* model, const adgs_time_basis* basi
     a.tb = *basis;
     a.out = *out;
     a.render = 0;
-    fused_forward_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
-    count_launch(1);
+    launch_fused_forward(a, N, stream);
     return check_stage("trajectory forward", false, stream);
 }
 

@@ -1,5 +1,6 @@
 // Optional per-stage CUDA-event timing and launch counting (bench.py's roofline leg).
 // Disabled by default: when off, a stage scope costs one predictable branch.
+#include <cstdlib>
 #include <vector>
 #include "api_internal.cuh"
 
@@ -21,6 +22,12 @@ static const char* kStageNames[kNumStages] = {"per_gaussian_forward", "depth_sor
 void count_launch(int n)
 {
     g_launches += (unsigned long long)n;
+}
+
+int tune_variant(const char* env_name, int dflt)
+{
+    const char* v = getenv(env_name);
+    return (v && *v) ? atoi(v) : dflt;
 }
 
 static cudaEvent_t get_event()

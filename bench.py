@@ -316,6 +316,35 @@ def run_ours(args):
 
     copy_stream = torch.cuda.Stream(device=device)
 
+    # device -> host read of the step's metric: an asynchronous copy into pinned memory that the host
+    # consumes one step later (after the next step has been queued), the way a training loop logs its
+    # loss without draining the GPU. Every step's value is read inside the timed region; the last one
+    # is drained before the closing event. --e2e-blocking restores the read-then-launch order.
+    metric_ring = [torch.empty((1,), dtype=torch.float32).pin_memory() for _ in range(2)]
+    metric_pending = []
+    metric_log = []
+
+    def consume_metric():
+        buf, ev = metric_pending.pop(0)
+        ev.synchronize()
+        metric_log.append(float(buf[0]))
+
+    def read_metric(value_on_device):
+        if args.e2e_blocking:
+            metric_log.append(float(value_on_device.item()))
+            return
+        buf = metric_ring[(len(metric_log) + len(metric_pending)) % 2]   # alternate: at most two reads in flight
+        buf.copy_(value_on_device.reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        metric_pending.append((buf, ev))
+        if len(metric_pending) > 1:
+            consume_metric()
+
+    def drain_metrics():
+        while metric_pending:
+            consume_metric()
+
     def e2e_step_exchange():
         dcam = host_cam.to(device, non_blocking=True)
         views_ = list(all_views)
@@ -335,7 +364,7 @@ def run_ours(args):
             return split_cot(flat)
 
         ex.run(views_, cots, pipe)
-        return float(box["res"]["img_opacity"].mean().item())
+        read_metric(box["res"]["img_opacity"].mean())
 
     def e2e_step():
         if ex is not None:
@@ -363,23 +392,28 @@ def run_ours(args):
             model._grad_sink = None
         if mv is not None:
             mv.bucket.all_reduce()
-        return float(res["img_opacity"].mean().item())   # device -> host read of a metric
+        read_metric(res["img_opacity"].mean())   # device -> host read of a metric
 
     for _ in range(3):
         e2e_step()
+    drain_metrics()
     barrier()
     e0.record()
     for _ in range(args.steps):
         e2e_step()
+    drain_metrics()
     e1.record()
     barrier()
+    assert len(metric_log) == args.steps + 3 and all(math.isfinite(v) for v in metric_log)
     ms_e2e = e0.elapsed_time(e1) / args.steps
     if world > 1:
         tt = torch.tensor([ms_e2e], device=device)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_e2e = float(tt.item())
     e2e = {"value": round(world * px / (ms_e2e * 1e-3) / 1e6, 2), "unit": "Mpix/s", "ms_per_step": round(ms_e2e, 4),
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "readback": "blocking .item() every step" if args.e2e_blocking else
+                       "async copy to pinned memory every step, consumed one step later; drained inside the timed region"}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -535,6 +569,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti-375x1242-1M", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-blocking", action="store_true", help="e2e: block on the metric read before queuing the next step")
     ap.add_argument("--parallel", default="exchange", choices=["exchange", "allreduce"],
                     help="multi-GPU data path (N > 1): splat exchange (default) or replicated model + gradient all-reduce")
     args = ap.parse_args()
