@@ -144,7 +144,7 @@ class TimeBasis(C.Structure):
         ("t", C.c_float),
         ("use_time_mask", C.c_int32),
         ("has_flow", C.c_int32),
-        ("_pad", C.c_int32),
+        ("sparse_grads", C.c_int32),
     ]
 
 
@@ -189,6 +189,26 @@ class Splats(C.Structure):
         ("mean_y", C.c_void_p),
     ]
 
+
+class AdamSegment(C.Structure):
+    _fields_ = [
+        ("param", C.c_void_p),
+        ("grad", C.c_void_p),
+        ("exp_avg", C.c_void_p),
+        ("exp_avg_sq", C.c_void_p),
+        ("n", C.c_int64),
+        ("split", C.c_int64),
+        ("plane", C.c_int64),
+        ("active", C.c_uint64 * 2),
+        ("lr_a", C.c_double),
+        ("lr_b", C.c_double),
+        ("lr_rule", C.c_int32),
+        ("_pad", C.c_int32),
+    ]
+
+
+ADAM_MAX_SEGMENTS = 16
+ADAM_LR_UNIFORM, ADAM_LR_SPLIT, ADAM_LR_SH4 = 0, 1, 2
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
 
@@ -247,6 +267,8 @@ SIGNATURES = {
     "adgs_shard_backward_multi": (C.c_int, [C.c_int32, _P(Camera), _P(Model), _P(TimeBasis), _P(C.c_void_p),
                                             _P(C.c_void_p), _P(C.c_void_p), _P(Model), C.c_int32, _P(C.c_void_p),
                                             C.c_void_p, C.c_void_p]),
+    "adgs_adam_step": (C.c_int, [_P(AdamSegment), C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int64,
+                                 C.c_void_p]),
     "adgs_launch_count": (C.c_ulonglong, []),
     "adgs_profile_begin": (C.c_int, []),
     "adgs_profile_num_stages": (C.c_int, []),

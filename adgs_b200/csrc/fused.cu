@@ -1154,6 +1154,7 @@ int run_per_gaussian_backward(const adgs_camera* cam, const adgs_model* model, c
     const int N = model->N_scene + model->N_obj;
     const int No = model->N_obj;
     int st;
+    if (basis->sparse_grads && accumulate) return ADGS_ERR_ARG;  // unwritten planes cannot be accumulated into
     {
         // dense-gradient semantics: everything outside the active columns is zero. The kernels write
         // every active plane in full, so only the complement is memset (plane = all objects of a
@@ -1187,7 +1188,7 @@ int run_per_gaussian_backward(const adgs_camera* cam, const adgs_model* model, c
                 c = e;
             }
         };
-        if (!accumulate) {
+        if (!accumulate && !basis->sparse_grads) {
             zero_inactive(grads->xyz_deform, basis->xyz, 0, 0, (size_t)3 * No);
             zero_inactive(grads->rot_deform, basis->rotation, basis->quat.start,
                           basis->quat.n_ctrl ? basis->quat.k + 1 : 0, (size_t)4 * No);

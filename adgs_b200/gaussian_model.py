@@ -212,26 +212,84 @@ class GaussianModel(nn.Module):
         m.active_sh_degree = sh_degree
         return m
 
-    def to_reference(self, grads=False) -> dict:
-        """Inverse of from_reference (parameters, or their .grad when grads=True)."""
-        pick = (lambda p: p.grad) if grads else (lambda p: p.detach())
+    def reference_layout(self, t: dict) -> dict:
+        """Planar arrays (keys = PARAM_NAMES, e.g. parameters, gradients or optimizer moments) -> the
+        reference's tensors by attribute name (inverse of planar_layout)."""
         ns, n = self.n_scene, self.n_scene + self.n_obj
-        xyz, sc, rot, op = pick(self.xyz), pick(self.scaling), pick(self.rotation), pick(self.opacity)
-        shs = pick(self.sh4).permute(1, 0, 2).reshape(n, 16, 3)
+        xyz, sc, rot, op = t["xyz"], t["scaling"], t["rotation"], t["opacity"]
+        shs = t["sh4"].permute(1, 0, 2).reshape(n, 16, 3)
         cs = get_param_num(self.order_args['shs'])
-        shsd = pick(self.shs_deform4).permute(1, 0, 2).reshape(n, -1)[:, :3 * cs].reshape(n, 3, cs)
-        out = dict(
+        shsd = t["shs_deform4"].permute(1, 0, 2).reshape(n, -1)[:, :3 * cs].reshape(n, 3, cs)
+        return dict(
             scene_xyz=xyz[:ns], obj_xyz=xyz[ns:], scene_scaling=sc[:ns], obj_scaling=sc[ns:],
             scene_rotation=rot[:ns], obj_rotation=rot[ns:], scene_opacity=op[:ns], obj_opacity=op[ns:],
             scene_shs_dc=shs[:ns, 0:1], obj_shs_dc=shs[ns:, 0:1], scene_shs_rest=shs[:ns, 1:], obj_shs_rest=shs[ns:, 1:],
             shs_deform_param_scene=shsd[:ns], shs_deform_param_obj=shsd[ns:],
-            xyz_deform_param=pick(self.xyz_deform).permute(2, 1, 0),
-            rotation_deform_param=pick(self.rot_deform).permute(1, 2, 0),
-            background_deform_param=pick(self.background_deform).reshape(1, 3, -1),
-            gs_time_sigma=pick(self.gs_time_sigma))
+            xyz_deform_param=t["xyz_deform"].permute(2, 1, 0),
+            rotation_deform_param=t["rot_deform"].permute(1, 2, 0),
+            background_deform_param=t["background_deform"].reshape(1, 3, -1),
+            gs_time_sigma=t["gs_time_sigma"])
+
+    def planar_layout(self, ref: dict) -> dict:
+        """The reference's tensors by attribute name -> planar arrays (keys = PARAM_NAMES)."""
+        dev = self.xyz.device
+        g = lambda k: ref[k].detach().to(device=dev, dtype=torch.float32)
+        cat = lambda a, b: torch.cat([g(a), g(b)], dim=0)
+        n = self.n_scene + self.n_obj
+        shs = torch.cat([cat("scene_shs_dc", "obj_shs_dc"), cat("scene_shs_rest", "obj_shs_rest")], dim=1)
+        shsd = cat("shs_deform_param_scene", "shs_deform_param_obj").reshape(n, -1)
+        pad = (-shsd.shape[1]) % 4
+        if pad:
+            shsd = torch.cat([shsd, shsd.new_zeros(n, pad)], dim=1)
+        out = dict(
+            xyz=cat("scene_xyz", "obj_xyz"), scaling=cat("scene_scaling", "obj_scaling"),
+            rotation=cat("scene_rotation", "obj_rotation"), opacity=cat("scene_opacity", "obj_opacity"),
+            sh4=shs.reshape(n, 12, 4).permute(1, 0, 2), shs_deform4=shsd.reshape(n, -1, 4).permute(1, 0, 2),
+            xyz_deform=g("xyz_deform_param").permute(2, 1, 0), rot_deform=g("rotation_deform_param").permute(2, 0, 1),
+            background_deform=g("background_deform_param").reshape(3, -1), gs_time_sigma=g("gs_time_sigma"))
+        return {k: v.contiguous() for k, v in out.items()}
+
+    def to_reference(self, grads=False) -> dict:
+        """Inverse of from_reference (parameters, or their .grad when grads=True)."""
+        pick = (lambda p: p.grad) if grads else (lambda p: p.detach())
+        out = self.reference_layout({k: pick(getattr(self, k)) for k in PARAM_NAMES})
         if not grads:
             out["gs_time"] = self.gs_time.reshape(-1, 1)
         return out
+
+    # ---- optimizer (scene/gaussian_model.py:337-413), see adgs_b200/optimizer.py ------------------------
+    def training_setup(self, training_args, window_aware=False):
+        from .optimizer import training_setup
+        return training_setup(self, training_args, window_aware=window_aware)
+
+    def update_learning_rate(self, iteration):
+        from .optimizer import update_learning_rate
+        update_learning_rate(self, iteration)
+
+    def _note_active_columns(self, tb):
+        """Control-point columns the backward of this render writes (window-aware optimizer step)."""
+        act = self.__dict__.setdefault("_active_cols", {"xyz": set(), "rotation": set(), "backwards": 0})
+        act["xyz"].update(tb.xyz.col[i] for i in range(tb.xyz.n))
+        act["rotation"].update(tb.rotation.col[i] for i in range(tb.rotation.n))
+        if tb.quat.n_ctrl:
+            act["rotation"].update(range(tb.quat.start, tb.quat.start + tb.quat.k + 1))
+        act["backwards"] += 1
+
+    def active_columns(self):
+        act = self.__dict__.get("_active_cols")
+        if act is None or act["backwards"] == 0:
+            raise RuntimeError("window-aware optimizer step without a render backward since the last step")
+        return {"xyz": sorted(act["xyz"]), "rotation": sorted(act["rotation"])}
+
+    def reset_active_columns(self):
+        self.__dict__["_active_cols"] = {"xyz": set(), "rotation": set(), "backwards": 0}
+
+    @property
+    def sparse_deform_grads(self):
+        """True while a window-aware optimizer owns the gradients: render backward then leaves inactive
+        control-point planes unwritten (one backward per optimizer step only)."""
+        opt = self.__dict__.get("optimizer")
+        return bool(opt is not None and getattr(opt, "window_aware", False))
 
     def shard(self, rank: int, world: int):
         """Rank `rank`'s slice of the model for the splat-exchange multi-GPU path: contiguous blocks of

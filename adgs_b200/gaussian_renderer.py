@@ -136,6 +136,13 @@ class _FusedRender(torch.autograd.Function):
                               dL_dsemantic=L.ptr(cot[3]) if ctx.render_objmask else None,
                               dL_dopacity=L.ptr(cot[4]))
             scratch = torch.empty((lib.adgs_render_scratch_bytes(N, model.n_obj),), dtype=torch.uint8, device=dev)
+            # window-aware optimizer: inactive control-point planes stay unwritten (no zero-fill); the
+            # optimizer reads only the columns recorded here
+            sparse = model.sparse_deform_grads and sink is None
+            if sparse and model.__dict__.get("_active_cols", {}).get("backwards", 0) > 0:
+                raise RuntimeError("window-aware FusedAdam supports one render backward per optimizer step")
+            model._note_active_columns(tb)
+            tb.sparse_grads = int(sparse)
             st = lib.adgs_render_backward(C.byref(cam), C.byref(cm), C.byref(tb), int(ctx.render_objmask),
                                           L.ptr(radii), L.ptr(geom), L.ptr(binning), int(ctx.capacity), L.ptr(img),
                                           L.ptr(saved), L.ptr(img_opacity), C.byref(ig), C.byref(gm),

@@ -34,6 +34,11 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # BASELINE.json configs[1]: KITTI-MOT-shaped frame, 1M Gaussians (25 % objects, 32 control points)
     "kitti-375x1242-1M": dict(W=1242, H=375, n=1_000_000, obj_frac=0.25, median_radius_px=3.0),
+    # BASELINE.json configs[2]: one camera of the Waymo-shaped rig, 3M Gaussians (parity / robustness runs, not the bench line)
+    "waymo-1066x1600-3M": dict(W=1600, H=1066, n=3_000_000, obj_frac=0.25, median_radius_px=3.0),
+    # BASELINE.json configs[4]: stress -- 10M Gaussians, median radius 12 px, half of them inside 5 % of the screen
+    "stress-1920x1280-10M": dict(W=1920, H=1280, n=10_000_000, obj_frac=0.25, median_radius_px=12.0, cluster=(0.5, 0.05)),
+    "stress-1920x1280-2M": dict(W=1920, H=1280, n=2_000_000, obj_frac=0.25, median_radius_px=12.0, cluster=(0.5, 0.05)),
     # smaller variants for quick checks
     "kitti-375x1242-200k": dict(W=1242, H=375, n=200_000, obj_frac=0.25, median_radius_px=3.0),
     "tiny": dict(W=320, H=192, n=20_000, obj_frac=0.25, median_radius_px=3.0),
@@ -133,7 +138,7 @@ def build_ours(wl, device, seed=0):
     n, n_obj = wl["n"], int(wl["n"] * wl["obj_frac"])
     n_scene = n - n_obj
     cam0 = scenes.make_camera(wl["W"], wl["H"], 90.0, time=T_CAMERA)
-    cloud = scenes.random_cloud(n, cam0, seed=seed, median_radius_px=wl["median_radius_px"])
+    cloud = scenes.random_cloud(n, cam0, seed=seed, median_radius_px=wl["median_radius_px"], cluster=wl.get("cluster"))
     tensors = scenes.random_model_tensors(n_scene, n_obj, scenes.BENCH_ORDER_ARGS, cloud, seed=seed + 1, device=device)
     model = GaussianModel.from_reference(tensors, scenes.BENCH_ORDER_ARGS, device=device)
     del tensors
@@ -415,6 +420,30 @@ def run_ours(args):
            "readback": "blocking .item() every step" if args.e2e_blocking else
                        "async copy to pinned memory every step, consumed one step later; drained inside the timed region"}
 
+    # ---- the step right after the path: fused Adam over all 18 parameter groups, timed on
+    #      its own (NOT part of `value`): 28 B per parameter element (p, g, m, v read; p, m, v written) -------
+    adam = None
+    if ex is None and mv is None:
+        from adgs_b200.optimizer import FusedAdam, GROUP_NAMES
+        res = step()
+        opt = FusedAdam(model, {n: 1e-4 for n in GROUP_NAMES}, eps=1e-15)
+        n_el = sum(p.numel() for p in params)
+        for _ in range(3):
+            opt.step()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            opt.step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_adam = e0.elapsed_time(e1) / 10
+        peak, _src = measured_hbm_peak()
+        adam = {"ms_per_step": round(ms_adam, 4), "elements": n_el, "algorithmic_bytes": n_el * 28,
+                "achieved_GBps": round(n_el * 28 / (ms_adam * 1e-3) / 1e9, 1),
+                "frac_of_hbm_peak": round(n_el * 28 / (ms_adam * 1e-3) / 1e9 / peak, 4),
+                "note": "adgs_adam_step, one launch for the reference's 18 groups; not included in value/e2e"}
+        del opt, res
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline()
@@ -434,7 +463,7 @@ def run_ours(args):
             "gaussians_per_s": round(gauss, 1),
             "e2e": e2e, "gpu_launches": round(launches, 1), "clocks": clocks,
             "roofline": roof, "step_roofline": step_roof, "stage_ms": {k: round(v, 4) for k, v in (stage_ms or {}).items()},
-            "cpu_baseline": cpu_base,
+            "cpu_baseline": cpu_base, "optimizer_step": adam,
         }
         print(json.dumps(line))
     if world > 1:
@@ -500,7 +529,7 @@ def run_reference(args):
         n, n_obj = wl["n"], int(wl["n"] * wl["obj_frac"])
         n_scene = n - n_obj
         cam0 = scenes.make_camera(wl["W"], wl["H"], 90.0, time=T_CAMERA)
-        cloud = scenes.random_cloud(n, cam0, seed=0, median_radius_px=wl["median_radius_px"])
+        cloud = scenes.random_cloud(n, cam0, seed=0, median_radius_px=wl["median_radius_px"], cluster=wl.get("cluster"))
         tensors = scenes.random_model_tensors(n_scene, n_obj, scenes.BENCH_ORDER_ARGS, cloud, seed=1, device=device)
         for k, v in tensors.items():
             if k != "gs_time":

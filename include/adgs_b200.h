@@ -259,7 +259,10 @@ typedef struct adgs_time_basis {
     float t;                   /* camera time (time mask, gaussian_model.py:207-214) */
     int32_t use_time_mask;
     int32_t has_flow;          /* evaluate xyz at the second time too (gaussian_renderer/__init__.py:54-57) */
-    int32_t _pad;
+    int32_t sparse_grads;      /* backward only, != 0: leave the gradient planes of control-point columns that are
+                                * inactive at this time UNWRITTEN instead of zero-filling them; the caller's
+                                * optimizer must then be window-aware (adgs_adam_segment.active). Not valid
+                                * together with accumulate != 0. */
 } adgs_time_basis;
 
 /* Parameter storage of the B200-native model (host container: adgs_b200/gaussian_model.py).
@@ -392,6 +395,40 @@ ADGS_API int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cam
                               char* const* shard_states, const float* const* grad_records,
                               const adgs_model* grads, int32_t accumulate, float* const* dL_dmeans2D,
                               char* scratch, adgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizer step: replaces `gaussians.optimizer.step()` of train.py:163-167
+ * for the torch.optim.Adam(l, lr=0.0, eps=1e-15) that GaussianModel.training_setup builds over 18
+ * parameter groups (scene/gaussian_model.py:346-372). One launch updates every array of adgs_model;
+ * groups that share an array (scene / object rows of xyz, DC / rest coefficients of the SH block)
+ * differ only in their learning rate, expressed as a per-element rule:
+ *   ADGS_ADAM_LR_UNIFORM  lr_a everywhere
+ *   ADGS_ADAM_LR_SPLIT    lr_a for elements [0, split), lr_b behind            (xyz: split = 3 * N_scene)
+ *   ADGS_ADAM_LR_SH4      lr_a for elements i < split with i % 4 != 3, else lr_b (sh4: split = 4 * N; the
+ *                         DC coefficient is floats 0..2 of chunk 0 of the (12,N,4) layout)
+ * `plane` > 0 declares the array as column planes of `plane` floats (control-point arrays): bit c of
+ * `active` set = the backward wrote column c; for every other column (c < 128) the gradient is taken
+ * as zero without being read (dense-Adam semantics without the zero-fill). plane = 0: read everything.
+ * `step` is the 1-based step count (bias correction), shared by all segments.
+ * ---------------------------------------------------------------------------------------- */
+#define ADGS_ADAM_MAX_SEGMENTS 16
+enum { ADGS_ADAM_LR_UNIFORM = 0, ADGS_ADAM_LR_SPLIT = 1, ADGS_ADAM_LR_SH4 = 2 };
+typedef struct adgs_adam_segment {
+    float* param;        /* device, n floats, updated in place */
+    const float* grad;   /* device, n floats */
+    float* exp_avg;      /* device, n floats (first moment), updated in place */
+    float* exp_avg_sq;   /* device, n floats (second moment), updated in place */
+    int64_t n;
+    int64_t split;
+    int64_t plane;
+    uint64_t active[2];
+    double lr_a;
+    double lr_b;
+    int32_t lr_rule;
+    int32_t _pad;
+} adgs_adam_segment;
+ADGS_API int adgs_adam_step(const adgs_adam_segment* segments, int32_t num_segments, double beta1, double beta2,
+                            double eps, int64_t step, adgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): cumulative number of kernels launched by the library, and
