@@ -332,14 +332,14 @@ def run_ours(args):
     def consume_metric():
         buf, ev = metric_pending.pop(0)
         ev.synchronize()
-        metric_log.append(float(buf[0]))
+        metric_log.append(float(buf[0].item()))
 
     def read_metric(value_on_device):
         if args.e2e_blocking:
-            metric_log.append(float(value_on_device.item()))
+            metric_log.append(float(value_on_device.detach().item()))
             return
         buf = metric_ring[(len(metric_log) + len(metric_pending)) % 2]   # alternate: at most two reads in flight
-        buf.copy_(value_on_device.reshape(1), non_blocking=True)
+        buf.copy_(value_on_device.detach().reshape(1), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(device))
         metric_pending.append((buf, ev))
