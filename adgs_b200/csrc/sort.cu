@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) radix_histogram_kernel(const uint32_t* __
 }
 
 template <bool IOTA>
-__global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
+__global__ void __launch_bounds__(kSortThreads, 4) onesweep_pass_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n_max,
     const uint32_t* __restrict__ d_n, int shift, uint32_t digit_mask, const uint32_t* __restrict__ hist,
@@ -181,14 +181,24 @@ __global__ void __launch_bounds__(kSortThreads) onesweep_pass_kernel(
             st_volatile_u32(my_status, kFlagPrefix | block_count);
         } else {
             st_volatile_u32(my_status, kFlagAgg | block_count);
-            const uint32_t* p = my_status - kRadix;
-            while (true) {
-                const uint32_t s = ld_volatile_u32(p);
-                const uint32_t f = s & kFlagMask;
-                if (f == 0) continue;
-                excl += s & kValueMask;
-                if (f == kFlagPrefix) break;
-                p -= kRadix;
+            // look back with four predecessor words in flight: the walk is a chain of L2 round trips,
+            // and a tile deep in the grid may have to sum many aggregates before it meets a prefix
+            int back = (int)tile - 1;  // nearest predecessor not yet accounted for
+            bool done = false;
+            while (!done) {
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    w[j] = (back - j >= 0) ? ld_volatile_u32(status + (size_t)(back - j) * kRadix + tid) : 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (done) break;
+                    const uint32_t f = w[j] & kFlagMask;
+                    if (f == 0) break;  // not published yet: reload from here
+                    excl += w[j] & kValueMask;
+                    --back;
+                    if (f == kFlagPrefix) done = true;
+                }
             }
             st_volatile_u32(my_status, kFlagPrefix | (excl + block_count));
         }
@@ -255,24 +265,34 @@ __global__ void __launch_bounds__(kScanThreads) scan_gather_kernel(const uint32_
         }
         uint32_t total;
         const uint32_t excl = block_exclusive_scan_256(sum, s_warp_scan, total);
-        if (tid == 0) {
+        if (tid < 32) {
+            // warp-parallel look-back: lane l inspects tile - 1 - l of the current 32-tile window
             uint32_t prefix = 0;
             if (tile == 0) {
-                st_volatile_u32(st + tile, kFlagPrefix | total);
+                if (tid == 0) st_volatile_u32(st + tile, kFlagPrefix | total);
             } else {
-                st_volatile_u32(st + tile, kFlagAgg | total);
+                if (tid == 0) st_volatile_u32(st + tile, kFlagAgg | total);
                 int p = (int)tile - 1;
                 while (true) {
-                    const uint32_t s = ld_volatile_u32(st + p);
-                    const uint32_t f = s & kFlagMask;
-                    if (f == 0) continue;
-                    prefix += s & kValueMask;
-                    if (f == kFlagPrefix) break;
-                    --p;
+                    const int q = p - (int)tid;
+                    uint32_t sv = kFlagPrefix;  // lanes before tile 0 act as an empty prefix
+                    if (q >= 0) {
+                        do {
+                            sv = ld_volatile_u32(st + q);
+                        } while ((sv & kFlagMask) == 0);
+                    }
+                    const uint32_t has_prefix = __ballot_sync(0xffffffffu, (sv & kFlagMask) == kFlagPrefix);
+                    const int stop = __ffs(has_prefix) - 1;  // nearest predecessor with an inclusive prefix (or -1)
+                    uint32_t v = (stop < 0 || (int)tid <= stop) ? (sv & kValueMask) : 0u;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    prefix += v;
+                    if (stop >= 0) break;
+                    p -= 32;
                 }
-                st_volatile_u32(st + tile, kFlagPrefix | (prefix + total));
+                if (tid == 0) st_volatile_u32(st + tile, kFlagPrefix | (prefix + total));
             }
-            s_prefix = prefix;
+            if (tid == 0) s_prefix = prefix;
         }
         __syncthreads();
         const uint32_t off = s_prefix + excl;
