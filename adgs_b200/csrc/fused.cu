@@ -126,7 +126,6 @@ __global__ void __launch_bounds__(TPB, MINB) fused_forward_kernel(const __grid_c
     const bool is_obj = g >= m.N_scene;
     const int j = g - m.N_scene;
     const bool flow = tb.has_flow != 0;
-
     // ---- position ------------------------------------------------------------------------
     float xt[3], xf[3];
 #pragma unroll
@@ -481,7 +480,8 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
 
 // Object rotation chain: normalised quaternion gradient -> static quaternion / linear terms /
 // control quaternions of the spline window. One forward sweep of the spline (cached) + one reverse.
-__global__ void __launch_bounds__(128) rotation_backward_kernel(const __grid_constant__ FusedBwdArgs a)
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) rotation_backward_kernel(const __grid_constant__ FusedBwdArgs a)
 {
     const adgs_model& m = a.m;
     const adgs_time_basis& tb = a.tb;
@@ -1219,7 +1219,15 @@ int run_per_gaussian_backward(const adgs_camera* cam, const adgs_model* model, c
     if ((st = check_stage("fused backward", debug, stream))) return st;
     if (No > 0) {
         StageScope sc(kStageRotationBwd, stream);
-        rotation_backward_kernel<<<(No + 127) / 128, 128, 0, stream>>>(a);
+        // sweep r1g (B200): 149 registers 0.086 ms, 128 registers 0.074 ms, 96 registers (some spills) 0.068 ms --
+        // a long dependent FP32 / MUFU chain per thread: more resident warps beat the spilled words
+        static const int rv = tune_variant("ADGS_TUNE_ROT", 0);
+        switch (rv) {
+        case 1: rotation_backward_kernel<128, 1><<<(No + 127) / 128, 128, 0, stream>>>(a); break;
+        case 2: rotation_backward_kernel<128, 6><<<(No + 127) / 128, 128, 0, stream>>>(a); break;
+        case 3: rotation_backward_kernel<128, 8><<<(No + 127) / 128, 128, 0, stream>>>(a); break;
+        default: rotation_backward_kernel<128, 5><<<(No + 127) / 128, 128, 0, stream>>>(a); break;
+        }
         count_launch(1);
     }
     if ((st = check_stage("rotation backward", debug, stream))) return st;

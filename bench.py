@@ -322,10 +322,10 @@ def run_ours(args):
     copy_stream = torch.cuda.Stream(device=device)
 
     # device -> host read of the step's metric: an asynchronous copy into pinned memory that the host
-    # consumes one step later (after the next step has been queued), the way a training loop logs its
+    # consumes two steps later (after the next two steps have been queued), the way a training loop logs its
     # loss without draining the GPU. Every step's value is read inside the timed region; the last one
     # is drained before the closing event. --e2e-blocking restores the read-then-launch order.
-    metric_ring = [torch.empty((1,), dtype=torch.float32).pin_memory() for _ in range(2)]
+    metric_ring = [torch.empty((1,), dtype=torch.float32).pin_memory() for _ in range(4)]
     metric_pending = []
     metric_log = []
 
@@ -338,12 +338,12 @@ def run_ours(args):
         if args.e2e_blocking:
             metric_log.append(float(value_on_device.detach().item()))
             return
-        buf = metric_ring[(len(metric_log) + len(metric_pending)) % 2]   # alternate: at most two reads in flight
+        buf = metric_ring[(len(metric_log) + len(metric_pending)) % 4]   # at most three reads in flight
         buf.copy_(value_on_device.detach().reshape(1), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(device))
         metric_pending.append((buf, ev))
-        if len(metric_pending) > 1:
+        if len(metric_pending) > 2:
             consume_metric()
 
     def drain_metrics():
@@ -418,7 +418,7 @@ def run_ours(args):
     e2e = {"value": round(world * px / (ms_e2e * 1e-3) / 1e6, 2), "unit": "Mpix/s", "ms_per_step": round(ms_e2e, 4),
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "readback": "blocking .item() every step" if args.e2e_blocking else
-                       "async copy to pinned memory every step, consumed one step later; drained inside the timed region"}
+                       "async copy to pinned memory every step, consumed two steps later; drained inside the timed region"}
 
     # ---- the step right after the path: fused Adam over all 18 parameter groups, timed on
     #      its own (NOT part of `value`): 28 B per parameter element (p, g, m, v read; p, m, v written) -------
