@@ -269,6 +269,11 @@ SIGNATURES = {
                                             C.c_void_p, C.c_void_p]),
     "adgs_adam_step": (C.c_int, [_P(AdamSegment), C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int64,
                                  C.c_void_p]),
+    "adgs_image_loss_partial_floats": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "adgs_image_loss_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 6 +
+                                [C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "adgs_image_loss_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 6 +
+                                 [C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "adgs_launch_count": (C.c_ulonglong, []),
     "adgs_profile_begin": (C.c_int, []),
     "adgs_profile_num_stages": (C.c_int, []),

@@ -444,6 +444,50 @@ def run_ours(args):
                 "note": "adgs_adam_step, one launch for the reference's 18 groups; not included in value/e2e"}
         del opt, res
 
+    # ---- the step right before the backward: fused L1 + SSIM image loss, forward + backward,
+    #      timed on its own against the torch composition the reference runs (utils/loss_utils.py:20-58) ----------
+    loss_fe = None
+    if ex is None and mv is None:
+        from adgs_b200 import losses as LS
+        gt_img = torch.rand(3, wl["H"], wl["W"], device=device)
+        pred_img = (gt_img + 0.1 * torch.randn_like(gt_img)).requires_grad_(True)
+
+        C3, Hh, Ww = 3, wl["H"], wl["W"]
+        planes = torch.empty((3, C3, Hh, Ww), device=device)
+        partial = torch.empty((lib.adgs_image_loss_partial_floats(C3, Hh, Ww),), device=device)
+        out3 = torch.empty((3,), device=device)
+        gone = torch.ones((1,), device=device)
+        d_img = torch.empty_like(gt_img)
+        stream_h = torch.cuda.current_stream(device).cuda_stream
+        pimg = pred_img.detach()
+
+        def fused_loss():
+            # the two C-ABI calls adgs_b200.losses.image_loss makes (forward incl. the derivative planes, backward)
+            lib.adgs_image_loss_forward(C3, Hh, Ww, pimg.data_ptr(), gt_img.data_ptr(), planes[0].data_ptr(),
+                                        planes[1].data_ptr(), planes[2].data_ptr(), partial.data_ptr(), 0.8, 0.2,
+                                        out3.data_ptr(), stream_h)
+            lib.adgs_image_loss_backward(C3, Hh, Ww, pimg.data_ptr(), gt_img.data_ptr(), planes[0].data_ptr(),
+                                         planes[1].data_ptr(), planes[2].data_ptr(), gone.data_ptr(), 0.8,
+                                         gone.data_ptr(), -0.2, d_img.data_ptr(), stream_h)
+
+        def time_it(fn, n=50):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+
+        ms_fused = time_it(fused_loss)
+        peak, _src = measured_hbm_peak()
+        nbytes = 3 * px * 4 * (2 + 3 + 5 + 1)   # fwd: img, gt read, 3 planes written; bwd: 5 planes read, 1 written
+        loss_fe = {"ms_fwd_bwd": round(ms_fused, 4), "algorithmic_bytes": nbytes,
+                   "achieved_GBps": round(nbytes / (ms_fused * 1e-3) / 1e9, 1),
+                   "note": "adgs_image_loss_forward/backward: (1-l)*L1 + l*(1-SSIM) on (3,H,W); not included in value/e2e"}
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline()
@@ -463,7 +507,7 @@ def run_ours(args):
             "gaussians_per_s": round(gauss, 1),
             "e2e": e2e, "gpu_launches": round(launches, 1), "clocks": clocks,
             "roofline": roof, "step_roofline": step_roof, "stage_ms": {k: round(v, 4) for k, v in (stage_ms or {}).items()},
-            "cpu_baseline": cpu_base, "optimizer_step": adam,
+            "cpu_baseline": cpu_base, "optimizer_step": adam, "loss_front_end": loss_fe,
         }
         print(json.dumps(line))
     if world > 1:

@@ -431,6 +431,26 @@ ADGS_API int adgs_adam_step(const adgs_adam_segment* segments, int32_t num_segme
                             double eps, int64_t step, adgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Loss front-end: the image term of train.py:79-80,113,
+ *   (1 - lambda_dssim) * lambda_l1 * l1_loss(image, gt) + lambda_dssim * (1 - ssim(image, gt)),
+ * replacing utils/loss_utils.py:l1_loss (:20-21) and ssim/_ssim (:35-58; window 11, sigma 1.5,
+ * zero padding 5, size_average=True). forward writes out3 = {mean |img - gt|, mean ssim,
+ * w_l1 * out3[0] + w_dssim * (1 - out3[1])} (device) and, when the three derivative planes (C,H,W each)
+ * are given, what backward needs; `partial` is scratch of adgs_image_loss_partial_floats(C,H,W) floats.
+ * backward takes the upstream gradients of the two means from DEVICE memory (0-d tensors; they may alias),
+ * each multiplied by a host-side weight: dL/d l1 = grad_l1[0] * w_l1, dL/d ssim = grad_ssim[0] * w_ssim,
+ * and writes dL/d img.
+ * ---------------------------------------------------------------------------------------- */
+ADGS_API size_t adgs_image_loss_partial_floats(int32_t C, int32_t H, int32_t W);
+ADGS_API int adgs_image_loss_forward(int32_t C, int32_t H, int32_t W, const float* img, const float* gt,
+                                     float* f_mu, float* f_e1, float* f_e12, float* partial, float w_l1,
+                                     float w_dssim, float* out3, adgs_stream_t stream);
+ADGS_API int adgs_image_loss_backward(int32_t C, int32_t H, int32_t W, const float* img, const float* gt,
+                                      const float* f_mu, const float* f_e1, const float* f_e12,
+                                      const float* grad_l1, float w_l1, const float* grad_ssim, float w_ssim,
+                                      float* d_img, adgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): cumulative number of kernels launched by the library, and
  * optional CUDA-event timing of each pipeline stage on the caller's stream.
  * adgs_profile_begin() arms it; adgs_profile_end() synchronises the recorded events and returns,
