@@ -207,6 +207,18 @@ class AdamSegment(C.Structure):
     ]
 
 
+class PixelLossInputs(C.Structure):
+    _fields_ = [
+        ("H", C.c_int32), ("W", C.c_int32),
+        ("depth", C.c_void_p), ("gt_depth", C.c_void_p), ("img_semantic", C.c_void_p), ("gt_semantic", C.c_void_p),
+        ("img_opacity", C.c_void_p), ("gt_sky", C.c_void_p), ("img_flow", C.c_void_p), ("flow", C.c_void_p),
+        ("flow_vis", C.c_void_p), ("flow_opacity", C.c_void_p),
+        ("K", C.c_float * 9), ("R", C.c_float * 9), ("T", C.c_float * 3),
+        ("flow_dist", C.c_float),
+        ("lambda_depth", C.c_float), ("lambda_obj", C.c_float), ("lambda_sky", C.c_float), ("lambda_flow", C.c_float),
+    ]
+
+
 ADAM_MAX_SEGMENTS = 16
 ADAM_LR_UNIFORM, ADAM_LR_SPLIT, ADAM_LR_SH4 = 0, 1, 2
 
@@ -274,6 +286,8 @@ SIGNATURES = {
                                 [C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "adgs_image_loss_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 6 +
                                  [C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "adgs_pixel_loss_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "adgs_pixel_loss": (C.c_int, [_P(PixelLossInputs), C.c_int32] + [C.c_void_p] * 8),
     "adgs_launch_count": (C.c_ulonglong, []),
     "adgs_profile_begin": (C.c_int, []),
     "adgs_profile_num_stages": (C.c_int, []),

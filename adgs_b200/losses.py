@@ -10,6 +10,8 @@ element-wise kernels and their autograd mirror images.
 Gradients flow to the first argument only (the rendered image), like in training where the ground
 truth is a constant. No fallback: the functions raise if the CUDA library is missing.
 """
+import ctypes as C
+
 import torch
 
 from . import _lib as L
@@ -111,3 +113,120 @@ def ssim(img1, img2, window_size=11, size_average=True):
 def image_loss(image, gt_image, lambda_dssim=0.2, lambda_l1=1.0):
     """(1 - lambda_dssim) * lambda_l1 * L1 + lambda_dssim * (1 - ssim), train.py:79-80,113."""
     return _WeightedImageLoss.apply(image, gt_image, (1.0 - lambda_dssim) * lambda_l1, lambda_dssim)
+
+
+# ---- per-pixel terms: depth, object mask, sky, flow (train.py:82-100) ---------------------------------------
+
+class _PixelLosses(torch.autograd.Function):
+    """(depth (H,W), img_semantic (1,H,W), img_opacity (H,W), img_flow (3,H,W)) ->
+    tensor (6,) = (depth, obj, sky, flow losses, lambda-weighted sum, selected flow pixels).
+    Gradients flow from element 4 (the weighted sum) only."""
+
+    @staticmethod
+    def forward(ctx, depth, img_semantic, img_opacity, img_flow, targets, lambdas):
+        lib = L.load()
+        ref = next(t for t in (depth, img_semantic, img_opacity, img_flow) if t is not None)
+        dev = ref.device
+        H, W = int(ref.shape[-2]), int(ref.shape[-1])
+        f32 = lambda t: None if t is None else t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        keep = dict(depth=f32(depth), sem=f32(img_semantic), opac=f32(img_opacity), flow_pts=f32(img_flow),
+                    gt_depth=f32(targets.get("gt_depth")), gt_sem=f32(targets.get("gt_semantic")),
+                    gt_sky=f32(targets.get("gt_sky")))
+        for k in ("depth", "sem", "opac", "flow_pts", "gt_depth", "gt_sem", "gt_sky"):
+            t = keep[k]
+            if t is not None and (t.shape[-2] != H or t.shape[-1] != W):
+                raise RuntimeError(f"pixel losses: {k} has shape {tuple(t.shape)}, expected (..., {H}, {W})")
+        inp = L.PixelLossInputs(H=H, W=W)
+        use_depth = keep["gt_depth"] is not None and keep["depth"] is not None and lambdas.get("depth", 0.0) > 0.0
+        use_obj = keep["gt_sem"] is not None and keep["sem"] is not None and lambdas.get("obj", 0.0) > 0.0
+        use_sky = keep["gt_sky"] is not None and keep["opac"] is not None and lambdas.get("sky", 0.0) > 0.0
+        flow_pkg = targets.get("flow_pkg")
+        use_flow = flow_pkg is not None and keep["flow_pts"] is not None and lambdas.get("flow", 0.0) > 0.0
+        if use_depth:
+            inp.depth, inp.gt_depth = keep["depth"].data_ptr(), keep["gt_depth"].data_ptr()
+        if use_obj:
+            inp.img_semantic, inp.gt_semantic = keep["sem"].data_ptr(), keep["gt_sem"].data_ptr()
+        if use_sky:
+            inp.img_opacity, inp.gt_sky = keep["opac"].data_ptr(), keep["gt_sky"].data_ptr()
+        if use_flow:
+            _, K, R, T, flow, flow_vis = flow_pkg
+            keep["flow"], keep["flow_vis"] = f32(flow), f32(flow_vis)
+            inp.img_flow, inp.flow, inp.flow_vis = keep["flow_pts"].data_ptr(), keep["flow"].data_ptr(), keep["flow_vis"].data_ptr()
+            if keep["opac"] is not None:
+                inp.flow_opacity = keep["opac"].data_ptr()
+            # small host matrices (the reference keeps K, R, T as 3x3 / 3 tensors in flow_pkg)
+            for name, src, n in (("K", K, 9), ("R", R, 9), ("T", T, 3)):
+                vals = [float(x) for x in torch.as_tensor(src).detach().reshape(-1).cpu().tolist()]
+                if len(vals) != n:
+                    raise RuntimeError(f"pixel losses: flow_pkg {name} must have {n} elements")
+                arr = getattr(inp, name)
+                for i, x in enumerate(vals):
+                    arr[i] = x
+            inp.flow_dist = float(targets.get("flow_dist", 1e-3))
+        inp.lambda_depth = float(lambdas.get("depth", 0.0)) if use_depth else 0.0
+        inp.lambda_obj = float(lambdas.get("obj", 0.0)) if use_obj else 0.0
+        inp.lambda_sky = float(lambdas.get("sky", 0.0)) if use_sky else 0.0
+        inp.lambda_flow = float(lambdas.get("flow", 0.0)) if use_flow else 0.0
+        scratch = torch.empty((lib.adgs_pixel_loss_scratch_bytes(H, W) // 8 + 1,), dtype=torch.float64, device=dev)
+        out = torch.empty((6,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = lib.adgs_pixel_loss(C.byref(inp), 1, scratch.data_ptr(), None, None, None, None, None, out.data_ptr(),
+                                     torch.cuda.current_stream(dev).cuda_stream)
+        L.check(st, "pixel_loss")
+        ctx.inp, ctx.keep, ctx.scratch, ctx.out = inp, keep, scratch, out
+        ctx.shapes = tuple(None if t is None else tuple(t.shape) for t in (depth, img_semantic, img_opacity, img_flow))
+        ctx.used = (use_depth, use_obj, use_sky or (use_flow and keep["opac"] is not None), use_flow)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = L.load()
+        inp, dev = ctx.inp, ctx.out.device
+        need = ctx.needs_input_grad[:4]
+        g_total = g[4:5].to(torch.float32).contiguous()
+        planes = []
+        for shape, used, nd in zip(ctx.shapes, ctx.used, need):
+            planes.append(torch.empty(shape, dtype=torch.float32, device=dev) if (shape is not None and used and nd)
+                          else None)
+        with torch.cuda.device(dev):
+            st = lib.adgs_pixel_loss(C.byref(inp), 2, ctx.scratch.data_ptr(), g_total.data_ptr(), L.ptr(planes[0]),
+                                     L.ptr(planes[1]), L.ptr(planes[2]), L.ptr(planes[3]), ctx.out.data_ptr(),
+                                     torch.cuda.current_stream(dev).cuda_stream)
+        L.check(st, "pixel_loss backward")
+        grads = []
+        for shape, p, nd in zip(ctx.shapes, planes, need):
+            if shape is None or not nd:
+                grads.append(None)
+            else:
+                grads.append(p if p is not None else torch.zeros(shape, dtype=torch.float32, device=dev))
+        return tuple(grads) + (None, None)
+
+
+def pixel_losses(depth=None, img_semantic=None, img_opacity=None, img_flow=None, gt_depth=None, gt_semantic=None,
+                 gt_sky=None, flow_pkg=None, flow_dist=1e-3, lambda_depth=0.0, lambda_obj=0.0, lambda_sky=0.0,
+                 lambda_flow=0.0):
+    """The per-pixel terms of train.py:82-100 in one call; a term is active when its lambda is > 0 and its
+    prediction and target are given (the reference's `if opt.lambda_* > 0.0` guards). Returns a dict with
+    'depth_loss', 'obj_loss', 'sky_loss', 'flow_loss' (detached values, for logging) and 'weighted' =
+    lambda_depth * depth + lambda_obj * obj + lambda_sky * sky + lambda_flow * flow (differentiable)."""
+    out = _PixelLosses.apply(depth, img_semantic, img_opacity, img_flow,
+                             dict(gt_depth=gt_depth, gt_semantic=gt_semantic, gt_sky=gt_sky, flow_pkg=flow_pkg,
+                                  flow_dist=flow_dist),
+                             dict(depth=lambda_depth, obj=lambda_obj, sky=lambda_sky, flow=lambda_flow))
+    d = out.detach()
+    return {"depth_loss": d[0], "obj_loss": d[1], "sky_loss": d[2], "flow_loss": d[3], "weighted": out[4],
+            "flow_pixels": d[5]}
+
+
+def get_depth_loss(pred, gt, mask=None):
+    """utils/loss_utils.py:60-65 (the training call passes no mask, train.py:86)."""
+    if mask is not None:
+        raise NotImplementedError("adgs_b200.losses.get_depth_loss implements the training call: mask=None")
+    return _PixelLosses.apply(pred, None, None, None, dict(gt_depth=gt), dict(depth=1.0))[4]
+
+
+def get_flow_loss(img_flow, flow_pkg, img_opacity=None, dist=1e-3):
+    """utils/loss_utils.py:88-108. Returns a 0-d tensor (0 when no pixel is selected, where the reference
+    returns the python float 0.0) -- and never synchronises with the host."""
+    return _PixelLosses.apply(None, None, img_opacity, img_flow, dict(flow_pkg=flow_pkg, flow_dist=dist),
+                              dict(flow=1.0))[4]

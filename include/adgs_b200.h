@@ -450,6 +450,40 @@ ADGS_API int adgs_image_loss_backward(int32_t C, int32_t H, int32_t W, const flo
                                       const float* grad_l1, float w_l1, const float* grad_ssim, float w_ssim,
                                       float* d_img, adgs_stream_t stream);
 
+/* The per-pixel terms of train.py:82-100: lambda_depth * get_depth_loss(depth, gt_depth)
+ * (utils/loss_utils.py:60-65, utils/depth_utils.py:3-45, mask = None) + lambda_obj * BCE(clip(img_semantic[0]),
+ * gt_semantic > 0) + lambda_sky * BCE(1 - clip(img_opacity), gt_sky) (train.py:91-99) + lambda_flow *
+ * get_flow_loss(img_flow, flow_pkg, img_opacity, dist) (utils/loss_utils.py:88-108, utils/flow_utils.py:5-10).
+ * A term is skipped when its ground-truth pointer is null. Three grid-stride passes, no host synchronisation
+ * (the reference's flow loss blocks on torch.nonzero): `phases` bit 0 = the two reduction passes (results stay
+ * in `scratch`), bit 1 = the plane pass; the forward of an autograd function runs phases = 1 (scalars only,
+ * planes null), its backward phases = 2 on the same scratch with the upstream gradient. Outputs: out6 = {depth, obj, sky, flow
+ * losses, their lambda-weighted sum, number of selected flow pixels}; and, for every non-null plane, the
+ * cotangent of the weighted sum times grad_total[0] (device scalar; null = 1): d_depth (H,W), d_semantic
+ * (H,W), d_opacity (H,W; sky + flow-weight paths), d_flow (3,H,W). Planes are (H,W) row-major, img_flow (3,H,W),
+ * flow (2,H,W) target pixel coordinates; K, R, T are HOST values (row-major 3x3, 3x3, 3).
+ * scratch: adgs_pixel_loss_scratch_bytes(H,W), 8-byte aligned. */
+typedef struct adgs_pixel_loss_inputs {
+    int32_t H, W;
+    const float* depth;         /* rendered (inverse) depth */
+    const float* gt_depth;
+    const float* img_semantic;  /* channel 0 of the rendered object mask */
+    const float* gt_semantic;
+    const float* img_opacity;   /* sky term */
+    const float* gt_sky;
+    const float* img_flow;      /* rendered flow points (3,H,W) */
+    const float* flow;          /* (2,H,W) */
+    const float* flow_vis;      /* (H,W) */
+    const float* flow_opacity;  /* (H,W) optional weight of the flow term (img_opacity), may be null */
+    float K[9], R[9], T[3];
+    float flow_dist;
+    float lambda_depth, lambda_obj, lambda_sky, lambda_flow;
+} adgs_pixel_loss_inputs;
+ADGS_API size_t adgs_pixel_loss_scratch_bytes(int32_t H, int32_t W);
+ADGS_API int adgs_pixel_loss(const adgs_pixel_loss_inputs* in, int32_t phases, char* scratch, const float* grad_total,
+                             float* d_depth, float* d_semantic, float* d_opacity, float* d_flow, float* out6,
+                             adgs_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): cumulative number of kernels launched by the library, and
  * optional CUDA-event timing of each pipeline stage on the caller's stream.
