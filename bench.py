@@ -488,6 +488,45 @@ def run_ours(args):
                    "achieved_GBps": round(nbytes / (ms_fused * 1e-3) / 1e9, 1),
                    "note": "adgs_image_loss_forward/backward: (1-l)*L1 + l*(1-SSIM) on (3,H,W); not included in value/e2e"}
 
+    # ---- a whole training iteration on the native pieces (render -> fused losses -> backward -> fused Adam,
+    #      adgs_b200/train_step.py = the inner part of train.py:74-167); runs last: it moves the parameters -----
+    train_it = None
+    if ex is None and mv is None:
+        from adgs_b200.train_step import training_iteration
+        targs = SimpleNamespace(percent_dense=0.01, object_extent=10.0, min_camera_extent=10.0, feature_lr=0.0025,
+                                opacity_lr=0.05, scaling_lr=0.005, rotation_lr=0.001, rotation_deform_lr=0.001,
+                                shs_deform_lr=0.0025, gs_time_sigma_lr=1e-2, position_lr_init=0.00016,
+                                position_lr_final=0.0000016, position_lr_delay_mult=0.01, position_lr_max_steps=60_000,
+                                position_deform_lr_scale=0.2, obj_position_lr_scale=0.8, scene_position_lr_scale=1.0)
+        topt = SimpleNamespace(lambda_dssim=0.2, lambda_l1=1.0, lambda_depth=0.1, lambda_flow=0.0, lambda_obj=0.1,
+                               lambda_sky=0.05, lambda_sigma=0.01)
+        Hh, Ww = wl["H"], wl["W"]
+        view = SimpleNamespace(image_height=Hh, image_width=Ww, FoVx=cam.FoVx, FoVy=cam.FoVy,
+                               world_view_transform=cam.world_view_transform, full_proj_transform=cam.full_proj_transform,
+                               camera_center=cam.camera_center, time=t, original_image=torch.rand(3, Hh, Ww, device=device),
+                               depth=torch.rand(Hh, Ww, device=device) + 0.1,
+                               semantic=(torch.rand(Hh, Ww, device=device) > 0.7).float(),
+                               sky=(torch.rand(Hh, Ww, device=device) > 0.8).float())
+        for p in params:
+            p.grad = None
+        per_mode = {}
+        for mode in ("dense", "window_aware"):
+            model.scene_extent = 20.0
+            model.training_setup(targs, window_aware=(mode == "window_aware"))
+            model.reset_active_columns()
+            for it in range(1, 6):
+                training_iteration(model, view, topt, pipe, it, frame_gap=1.0 / 96)
+            torch.cuda.synchronize()
+            e0.record()
+            for it in range(6, 6 + 20):
+                training_iteration(model, view, topt, pipe, it, frame_gap=1.0 / 96)
+            e1.record()
+            torch.cuda.synchronize()
+            per_mode[mode] = round(e0.elapsed_time(e1) / 20, 4)
+            model.optimizer = None
+        train_it = {"ms_per_iteration": per_mode, "note": "render + L1/SSIM/depth/obj/sky losses + backward + fused Adam "
+                    "(18 groups), one view per iteration like train.py; not part of value/e2e"}
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline()
@@ -507,7 +546,7 @@ def run_ours(args):
             "gaussians_per_s": round(gauss, 1),
             "e2e": e2e, "gpu_launches": round(launches, 1), "clocks": clocks,
             "roofline": roof, "step_roofline": step_roof, "stage_ms": {k: round(v, 4) for k, v in (stage_ms or {}).items()},
-            "cpu_baseline": cpu_base, "optimizer_step": adam, "loss_front_end": loss_fe,
+            "cpu_baseline": cpu_base, "optimizer_step": adam, "loss_front_end": loss_fe, "train_iteration": train_it,
         }
         print(json.dumps(line))
     if world > 1:
