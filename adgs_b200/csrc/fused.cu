@@ -625,7 +625,8 @@ struct MultiViewArgs {
     ViewIO v[kMaxViews];
 };
 
-__global__ void __launch_bounds__(256, 2) shard_forward_multi_kernel(const __grid_constant__ MultiViewArgs a)
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) shard_forward_multi_kernel(const __grid_constant__ MultiViewArgs a)
 {
     __shared__ CamSmem cam;
     __shared__ float s_bg[6];
@@ -758,7 +759,8 @@ __global__ void __launch_bounds__(256, 2) shard_forward_multi_kernel(const __gri
     }
 }
 
-__global__ void __launch_bounds__(128, 3) shard_backward_multi_kernel(const __grid_constant__ MultiViewArgs a)
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const __grid_constant__ MultiViewArgs a)
 {
     __shared__ CamSmem cam;
     __shared__ float s_wshs[kMaxViews][ADGS_MAX_TERMS * 2];  // dense SH-deform weights per view and column
@@ -954,7 +956,8 @@ __global__ void __launch_bounds__(128, 3) shard_backward_multi_kernel(const __gr
 
 // Rotation chain of the object Gaussians for every view of the batch; the control-quaternion windows
 // differ between views, so the (host zero-filled) planes are accumulated with read-modify-write.
-__global__ void __launch_bounds__(128) rotation_backward_multi_kernel(const __grid_constant__ MultiViewArgs a)
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) rotation_backward_multi_kernel(const __grid_constant__ MultiViewArgs a)
 {
     const adgs_model& m = a.m;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1532,7 +1535,7 @@ int adgs_shard_forward_multi(int32_t num_views, const adgs_camera* cams, const a
     }
     {
         StageScope sc(kStagePerGaussianFwd, stream);
-        shard_forward_multi_kernel<<<(N + 255) / 256, 256, 0, stream>>>(a);
+        shard_forward_multi_kernel<256, 2><<<(N + 255) / 256, 256, 0, stream>>>(a);  // sweep r1l: 128 registers best
         count_launch(1);
     }
     return check_stage("shard forward (multi-view)", cams[0].debug != 0, stream);
@@ -1597,13 +1600,15 @@ int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cams, const 
     int st;
     {
         StageScope scope(kStagePerGaussianBwd, stream);
-        shard_backward_multi_kernel<<<(N + 127) / 128, 128, 0, stream>>>(a);
+        // sweep r1l (2 GPUs): 168 registers 0.289 ms, 128 registers 0.244 ms, 230 registers 0.366 ms
+        shard_backward_multi_kernel<128, 4><<<(N + 127) / 128, 128, 0, stream>>>(a);
         count_launch(1);
     }
     if ((st = check_stage("shard backward (multi-view)", debug, stream))) return st;
     if (No > 0) {
         StageScope scope(kStageRotationBwd, stream);
-        rotation_backward_multi_kernel<<<(No + 127) / 128, 128, 0, stream>>>(a);
+        // sweep r1l: 199 registers 0.123 ms, 128 registers 0.084 ms, 96 registers 0.093 ms
+        rotation_backward_multi_kernel<128, 4><<<(No + 127) / 128, 128, 0, stream>>>(a);
         count_launch(1);
     }
     if ((st = check_stage("rotation backward (multi-view)", debug, stream))) return st;
