@@ -1030,6 +1030,78 @@ __global__ void __launch_bounds__(TPB, MINB) rotation_backward_multi_kernel(cons
     put4(reinterpret_cast<float4*>(a.g.rotation) + g, grot, a.accumulate);
 }
 
+// View-parallel variant for batches in which every view has a quaternion spline: one thread per
+// (object, view) -- blockIdx.y = view -- so a rank that owns N_obj / G objects still fills the GPU with
+// N_obj / G * V threads (at G = 8 the per-object loop over 8 views left 244 CTAs of serial work). The
+// per-view contributions to the control-quaternion planes meet in global memory with 16-byte vector REDs
+// on the host-zero-filled planes.
+__device__ __forceinline__ void red_add4(float4* p, const float4& v)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) rotation_backward_views_kernel(const __grid_constant__ MultiViewArgs a)
+{
+    const adgs_model& m = a.m;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m.N_obj) return;
+    const int g = m.N_scene + j;
+    const int vi = blockIdx.y;
+    const float4* rd = reinterpret_cast<const float4*>(m.rot_deform);
+    float4* grd = reinterpret_cast<float4*>(a.g.rot_deform);
+    // with a spline the static object quaternion is unused: its gradient is zero (written once, by view 0)
+    if (vi == 0) put4(reinterpret_cast<float4*>(a.g.rotation) + g, make_float4(0.f, 0.f, 0.f, 0.f), a.accumulate);
+    const ViewIO& V = a.v[vi];
+    const adgs_time_basis& tb = V.tb;
+    float4 qraw = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < tb.rotation.n; ++t) {
+        const float4 p = __ldg(rd + (size_t)tb.rotation.col[t] * m.N_obj + j);
+        const float w = tb.rotation.w0[t];
+        qraw.x += p.x * w;
+        qraw.y += p.y * w;
+        qraw.z += p.z * w;
+        qraw.w += p.w * w;
+    }
+    Quat qt[ADGS_MAX_QUAT_ORDER + 1], P[ADGS_MAX_QUAT_ORDER + 1], E[ADGS_MAX_QUAT_ORDER + 1];
+    float3 om[ADGS_MAX_QUAT_ORDER + 1];
+    float norms[ADGS_MAX_QUAT_ORDER + 1];
+    const int k = tb.quat.k;
+#pragma unroll
+    for (int i = 0; i <= ADGS_MAX_QUAT_ORDER; ++i) {
+        norms[i] = 1.f;
+        if (i <= k) {
+            qt[i] = ctrl_quat(__ldg(rd + (size_t)(tb.quat.start + i) * m.N_obj + j), norms[i]);
+        } else {
+            qt[i] = Quat{0.f, 0.f, 0.f, 1.f};
+        }
+    }
+    const Quat r = quat_spline_cached(qt, k, tb.quat.cum, P, E, om);
+    qraw.x += r.w;
+    qraw.y += r.x;
+    qraw.z += r.y;
+    qraw.w += r.z;
+    const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+    const float4 qhat = make_float4(qraw.x / qn, qraw.y / qn, qraw.z / qn, qraw.w / qn);
+    const float4 graw = normalize4_bwd(qhat, qn, V.dq_scratch[j]);  // wxyz
+    if (!grd) return;
+    for (int t = 0; t < tb.rotation.n; ++t) {
+        const float w = tb.rotation.w0[t];
+        red_add4(grd + (size_t)tb.rotation.col[t] * m.N_obj + j, make_float4(graw.x * w, graw.y * w, graw.z * w, graw.w * w));
+    }
+    Quat gqt[ADGS_MAX_QUAT_ORDER + 1];
+    quat_spline_bwd(qt, k, tb.quat.cum, P, E, om, Quat{graw.y, graw.z, graw.w, graw.x}, gqt);
+#pragma unroll
+    for (int i = 0; i <= ADGS_MAX_QUAT_ORDER; ++i) {
+        if (i <= k) {
+            const float4 nq = make_float4(qt[i].w, qt[i].x, qt[i].y, qt[i].z);
+            const float4 gg = make_float4(gqt[i].w, gqt[i].x, gqt[i].y, gqt[i].z);
+            red_add4(grd + (size_t)(tb.quat.start + i) * m.N_obj + j, normalize4_bwd(nq, norms[i], gg));
+        }
+    }
+}
+
 // background gradient from the per-view sums
 __global__ void background_finalize_multi_kernel(const __grid_constant__ MultiViewArgs a)
 {
@@ -1535,7 +1607,9 @@ int adgs_shard_forward_multi(int32_t num_views, const adgs_camera* cams, const a
     }
     {
         StageScope sc(kStagePerGaussianFwd, stream);
-        shard_forward_multi_kernel<256, 2><<<(N + 255) / 256, 256, 0, stream>>>(a);  // sweep r1l: 128 registers best
+        // 2-GPU sweep r1l: 128 registers best; 4-GPU sweep r1p: a view-parallel grid (one CTA per chunk and view)
+        // was slower (0.175-0.192 ms vs 0.168 ms) and was dropped
+        shard_forward_multi_kernel<256, 2><<<(N + 255) / 256, 256, 0, stream>>>(a);
         count_launch(1);
     }
     return check_stage("shard forward (multi-view)", cams[0].debug != 0, stream);
@@ -1608,7 +1682,14 @@ int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cams, const 
     if (No > 0) {
         StageScope scope(kStageRotationBwd, stream);
         // sweep r1l: 199 registers 0.123 ms, 128 registers 0.084 ms, 96 registers 0.093 ms
-        rotation_backward_multi_kernel<128, 4><<<(No + 127) / 128, 128, 0, stream>>>(a);
+        bool all_spline = a.g.rot_deform != nullptr;
+        for (int v = 0; v < num_views; ++v) all_spline = all_spline && bases[v].quat.n_ctrl != 0;
+        if (all_spline && num_views > 1) {
+            // per-(object, view) threads; single-GPU sweep r1g: 96 registers best for this chain
+            rotation_backward_views_kernel<128, 5><<<dim3((No + 127) / 128, num_views), 128, 0, stream>>>(a);
+        } else {
+            rotation_backward_multi_kernel<128, 4><<<(No + 127) / 128, 128, 0, stream>>>(a);
+        }
         count_launch(1);
     }
     if ((st = check_stage("rotation backward (multi-view)", debug, stream))) return st;

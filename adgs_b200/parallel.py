@@ -13,6 +13,8 @@ that a plain gradient sum does not cover (gaussian_model.py:863-867, train.py:15
 """
 from typing import Dict, List, Sequence
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -211,6 +213,17 @@ class SplatExchangeStep:
         stream = torch.cuda.current_stream(dev).cuda_stream
         results, stats = [], []
         first = True
+        timing = self.__dict__.setdefault("_timing", None)
+        if timing is None and os.environ.get("ADGS_EXCHANGE_TIMING"):
+            timing = self.__dict__["_timing"] = {"marks": [], "sums": {}, "count": 0}
+
+        def mark(name):
+            if timing is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(torch.cuda.current_stream(dev))
+                timing["marks"].append((name, ev))
+
+        mark("start")
         o = dict(dtype=torch.float32, device=dev)
         D_S = 1 if self.render_objmask else 0
         for rnd in range(len(views) // V):
@@ -237,6 +250,7 @@ class SplatExchangeStep:
                 L.check(lib.adgs_shard_forward_multi(V, cam_arr, C.byref(cmodel), basis_arr, int(self.render_objmask),
                                                      splat_arr, state_arr, stream), "shard_forward_multi")
                 radii = meta[:, 2]
+                mark("shard_forward")
                 # ---- splats travel to the rank that blends their view (chunk d of dim 0 -> rank d): the
                 #      20-byte binning state first, the 64-byte records behind it on the NCCL stream, so
                 #      that sorting and binning overlap the bulk of the transfer ---------------------------
@@ -246,6 +260,7 @@ class SplatExchangeStep:
                     w_meta = dist.all_to_all_single(r_meta, meta, group=self.group, async_op=True)
                     w_rec = dist.all_to_all_single(r_rec, rec, group=self.group, async_op=True)
                     w_meta.wait()
+                    mark("meta_all_to_all")
                 else:
                     r_meta, r_rec, w_rec = meta, rec, None
                 # (G, k, 5, n) -> per local view and plane, rank-major over the shards
@@ -296,10 +311,12 @@ class SplatExchangeStep:
                         binning, capacity = holder["b"], int(R)
                         self._capacity = max(self._capacity, int(1.3 * R) + 65536)
                         counters = ev = None
+                    mark("binning")
                     # ---- the records have (by now, mostly) arrived: blend ---------------------------------
                     if w_rec is not None:
                         w_rec.wait()
                         w_rec = None
+                    mark("record_all_to_all_wait")
                     s_rec = r_rec[:, i].reshape(P, 16)          # a plain view when k == 1
                     splats.record = s_rec.data_ptr()
                     L.check(lib.adgs_splats_blend(C.byref(cc), C.byref(splats), D_S, has_flow, C.byref(images),
@@ -309,6 +326,7 @@ class SplatExchangeStep:
                            "img_flow": img["flow"] if has_flow else None,
                            "img_semantic": img["semantic"] if self.render_objmask else None, "radii": s_radii}
                     results.append(res)
+                    mark("blend_forward")
                     # ---- blend backward of my view -> gradient records for every shard ------------------
                     cot = cotangent_fn((cam, flow_t), res)
                     ct = {kk: (None if cot.get(kk) is None else cot[kk].contiguous()) for kk in
@@ -328,8 +346,10 @@ class SplatExchangeStep:
                                                      grec.data_ptr(), stream), "splats_backward")
                     if k > 1:
                         gback[:, i] = grec.view(G, n, 16)
+                    mark("cotangents+blend_backward")
                 # ---- gradient records back to the owners; per-Gaussian backward of my shard: ONE launch ----
                 r_grec = self._all_to_all(gback.view(V, n, 16))
+                mark("gradient_all_to_all")
                 del r_meta
                 scratch = torch.empty((lib.adgs_shard_scratch_bytes(V, m.n_obj),), dtype=torch.uint8, device=dev)
                 gm = m.c_model_from(self.grads, with_time=False)
@@ -341,6 +361,7 @@ class SplatExchangeStep:
                                                       grec_arr, C.byref(gm), int(not first), d2_arr, L.ptr(scratch),
                                                       stream), "shard_backward_multi")
                 first = False
+                mark("shard_backward")
                 for v in range(V):
                     stats.append((d2[v], radii[v]))
         # the background trajectory is shared by every Gaussian: its gradient sums over the shards
@@ -348,4 +369,20 @@ class SplatExchangeStep:
             dist.all_reduce(self.grads["background_deform"], op=dist.ReduceOp.SUM, group=self.group)
         for name in self.names:
             getattr(m, name).grad = self.grads[name]
+        if timing is not None:
+            torch.cuda.synchronize(dev)
+            marks = timing["marks"]
+            timing["calls"] = timing.get("calls", 0) + 1
+            if timing["calls"] > 10:  # skip the warm-up calls (NCCL channel set-up, allocator growth)
+                for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+                    timing["sums"][n1] = timing["sums"].get(n1, 0.0) + e0.elapsed_time(e1)
+                timing["count"] += 1
+            timing["marks"] = []
         return results, stats
+
+    def timing_report(self):
+        """Mean milliseconds per phase of run() (set ADGS_EXCHANGE_TIMING=1; adds a device sync per step)."""
+        t = self.__dict__.get("_timing")
+        if not t or not t["count"]:
+            return None
+        return {k: round(v / t["count"], 4) for k, v in t["sums"].items()}

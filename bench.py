@@ -579,6 +579,8 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline()
 
+    if rank == 0 and ex is not None and ex.timing_report():
+        print("exchange phases (ms):", ex.timing_report(), file=sys.stderr)
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(mpix, 2), "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
