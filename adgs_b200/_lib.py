@@ -219,6 +219,11 @@ class PixelLossInputs(C.Structure):
     ]
 
 
+class EnvMap(C.Structure):
+    _fields_ = [("R", C.c_int32), ("C", C.c_int32), ("grid", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p),
+                ("exp_avg_sq", C.c_void_p), ("touched", C.c_void_p)]
+
+
 ADAM_MAX_SEGMENTS = 16
 ADAM_LR_UNIFORM, ADAM_LR_SPLIT, ADAM_LR_SH4 = 0, 1, 2
 
@@ -288,6 +293,10 @@ SIGNATURES = {
                                  [C.c_float, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "adgs_pixel_loss_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "adgs_pixel_loss": (C.c_int, [_P(PixelLossInputs), C.c_int32] + [C.c_void_p] * 8),
+    "adgs_env_touched_bytes": (C.c_size_t, [C.c_int32]),
+    "adgs_env_forward": (C.c_int, [_P(EnvMap), C.c_int32, C.c_int32, C.c_float] + [C.c_void_p] * 6),
+    "adgs_env_backward": (C.c_int, [_P(EnvMap), C.c_int32, C.c_int32, C.c_float] + [C.c_void_p] * 6),
+    "adgs_env_adam_step": (C.c_int, [_P(EnvMap), C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]),
     "adgs_launch_count": (C.c_ulonglong, []),
     "adgs_profile_begin": (C.c_int, []),
     "adgs_profile_num_stages": (C.c_int, []),

@@ -198,7 +198,10 @@ def render(viewpoint_camera, pc: GaussianModel, env_map, pipe, scaling_modifier=
         if materialize:
             deform_pkg.update(xyz=out[7], rotation=out[8], shs=out[9])
 
-    if env_map is not None:
+    if env_map is not None and hasattr(env_map, "composite"):
+        # adgs_b200.env.EnvironmentMap: background + blend in one kernel (gaussian_renderer/__init__.py:92-94)
+        rendered_image, background = env_map.composite(foreground, img_opacity, viewpoint_camera)
+    elif env_map is not None:
         background = env_map.get_image_background(viewpoint_camera)
         rendered_image = foreground + (1.0 - img_opacity) * background
     else:

@@ -485,6 +485,40 @@ ADGS_API int adgs_pixel_loss(const adgs_pixel_loss_inputs* in, int32_t phases, c
                              adgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Environment map: replaces EnvironmentMap.get_image_background /
+ * get_env_color (scene/env.py:44-76, rays :11-27, utils/graphics_utils.py:95-100), the composite
+ * `foreground + (1 - img_opacity) * background` (gaussian_renderer/__init__.py:92-94) and
+ * `env_map.optimizer.step()` (scene/env.py:78-83, train.py:165) for the (1,C,R,R) grid_map.
+ *   forward : background (C,H,W) and / or rendered = foreground + (1 - img_opacity) * background
+ *   backward: d img_opacity (H,W) written; texel gradients are ADDED into the persistent dense buffer
+ *             env->grad (zero-initialised once by the caller) and the 32x32-texel tiles they fall into are
+ *             marked in env->touched (adgs_env_touched_bytes(R) bytes, zero-initialised once);
+ *             d foreground = g_rendered (no kernel needed)
+ *   step    : Adam (torch.optim.Adam arithmetic, eps = 1e-15 in the reference) over the tiles ever touched,
+ *             zeroing their gradient in the same pass -- identical to the dense step, since a texel that
+ *             never received a gradient has zero moments and a zero update.
+ * `world_view_transform` = the camera's (4,4) tensor on the DEVICE; focal = W / (2 tan(FoVx / 2)).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct adgs_env_map {
+    int32_t R;            /* resolution (scene/env.py:31) */
+    int32_t C;            /* channels */
+    float* grid;          /* (1,C,R,R) parameter */
+    float* grad;          /* (1,C,R,R) persistent gradient buffer (backward, step) */
+    float* exp_avg;       /* (1,C,R,R) (step) */
+    float* exp_avg_sq;    /* (1,C,R,R) (step) */
+    uint8_t* touched;     /* adgs_env_touched_bytes(R) (backward, step) */
+} adgs_env_map;
+ADGS_API size_t adgs_env_touched_bytes(int32_t R);
+ADGS_API int adgs_env_forward(const adgs_env_map* env, int32_t H, int32_t W, float focal,
+                              const float* world_view_transform, const float* foreground, const float* img_opacity,
+                              float* background, float* rendered, adgs_stream_t stream);
+ADGS_API int adgs_env_backward(const adgs_env_map* env, int32_t H, int32_t W, float focal,
+                               const float* world_view_transform, const float* img_opacity, const float* g_rendered,
+                               const float* g_background, float* d_opacity, adgs_stream_t stream);
+ADGS_API int adgs_env_adam_step(const adgs_env_map* env, double lr, double beta1, double beta2, double eps,
+                                int64_t step, adgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): cumulative number of kernels launched by the library, and
  * optional CUDA-event timing of each pipeline stage on the caller's stream.
  * adgs_profile_begin() arms it; adgs_profile_end() synchronises the recorded events and returns,

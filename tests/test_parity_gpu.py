@@ -42,6 +42,8 @@ CASES = {
     "huge_splats": dict(n=1500, W=200, H=120, seed=7, median_radius_px=60.0),
     "scale_mod": dict(n=3000, W=128, H=80, seed=8, scale_modifier=0.6, yaw_deg=15.0),
     "medium": dict(n=200_000, W=640, H=360, seed=9),
+    # BASELINE.json configs[1] at full size, against the unmodified reference kernels
+    "kitti_full": dict(n=1_000_000, W=1242, H=375, seed=10, median_radius_px=3.0),
 }
 
 
