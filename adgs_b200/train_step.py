@@ -4,8 +4,8 @@
 `optimizer.FusedAdam` (one-launch Adam over the reference's 18 parameter groups).
 
 Not reproduced here (out of scope): densification / pruning, the near-index
-regularisers (lambda_reg, lambda_sigma_reg: they need `obj_near_idx` from pytorch3d knn_points), env-map
-optimisation, logging, checkpointing. `lambda_sigma`'s own term (train.py:105-107) is included because it
+regularisers (lambda_reg, lambda_sigma_reg: they need `obj_near_idx` from pytorch3d knn_points), logging,
+checkpointing. An `adgs_b200.env.EnvironmentMap` passed as `env_map` is composited by render() and stepped here. `lambda_sigma`'s own term (train.py:105-107) is included because it
 only touches `gs_time_sigma`.
 """
 import torch
@@ -42,6 +42,9 @@ def training_iteration(model, viewpoint_cam, opt, pipe, iteration, env_map=None,
     loss.backward()
     model.optimizer.step()
     model.optimizer.zero_grad(set_to_none=True)
+    if env_map is not None and getattr(env_map, "optimizer", None) is not None:   # train.py:165,167
+        env_map.optimizer.step()
+        env_map.optimizer.zero_grad(set_to_none=True)
     logs = {"total_loss": loss.detach(), "depth_loss": px["depth_loss"], "flow_loss": px["flow_loss"],
             "obj_loss": px["obj_loss"], "sky_loss": px["sky_loss"], "sigma_loss": sigma_loss}
     return logs, render_pkg

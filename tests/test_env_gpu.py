@@ -102,3 +102,61 @@ def test_render_uses_the_fused_composite():
     assert _rel(res["render"], expect.cpu().numpy()) <= 1e-4 and _rel(res["background"], bg.cpu().numpy()) <= 1e-4
     res["render"].sum().backward()
     assert float(env.grad_buffer.abs().max()) > 0.0 and model.opacity.grad is not None
+
+
+def test_env_map_iteration_cost_at_reference_resolution():
+    """8192^2 x 3 map (arguments/__init__.py:66-67), KITTI frame: composite + backward + optimizer step, fused
+    vs the reference's formulation (oracle = scene/env.py restated: grid_sample autograd + dense torch Adam).
+    Numbers go to gpurun_out/env_timing.json for profiles/."""
+    import json
+    from oracle import env_oracle as EO
+    R, H, W = 8192, 375, 1242
+    cam = _cam(H, W, 10.0)
+    fg = torch.rand(3, H, W, device="cuda", requires_grad=True)
+    op = torch.rand(1, H, W, device="cuda", requires_grad=True)
+    cot = torch.randn(3, H, W, device="cuda")
+
+    def timed(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    env = EnvironmentMap(R)
+    env.training_setup(SimpleNamespace(env_lr=1e-3))
+
+    def ours():
+        fg.grad = op.grad = None
+        rendered, _ = env.composite(fg, op, cam)
+        (rendered * cot).sum().backward()
+        env.optimizer.step()
+        env.optimizer.zero_grad(set_to_none=True)
+
+    ms_ours = timed(ours)
+    grid0 = env.grid_map.detach().clone()
+    del env
+    torch.cuda.empty_cache()
+    ref = torch.nn.Parameter(grid0)
+    ref_opt = torch.optim.Adam([{"params": [ref], "lr": 1e-3}], lr=0.0, eps=1e-15)
+
+    def reference():
+        fg.grad = op.grad = None
+        bg = EO.get_image_background(ref, cam.FoVx, H, W, cam.world_view_transform)
+        (EO.composite(fg, op, bg) * cot).sum().backward()
+        ref_opt.step()
+        ref_opt.zero_grad(set_to_none=True)
+
+    ms_ref = timed(reference)
+    out = {"resolution": R, "H": H, "W": W, "fused_ms_per_iteration": round(ms_ours, 4),
+           "torch_ms_per_iteration": round(ms_ref, 4), "speedup": round(ms_ref / ms_ours, 1)}
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if os.path.isdir(os.path.join(root, "gpurun_out")):
+        with open(os.path.join(root, "gpurun_out", "env_timing.json"), "w") as f:
+            json.dump(out, f)
+    assert ms_ours < ms_ref, out
