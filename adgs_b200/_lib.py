@@ -221,7 +221,7 @@ class PixelLossInputs(C.Structure):
 
 class EnvMap(C.Structure):
     _fields_ = [("R", C.c_int32), ("C", C.c_int32), ("grid", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p),
-                ("exp_avg_sq", C.c_void_p), ("touched", C.c_void_p)]
+                ("exp_avg_sq", C.c_void_p), ("touched", C.c_void_p), ("tile_list", C.c_void_p)]
 
 
 ADAM_MAX_SEGMENTS = 16
@@ -294,6 +294,7 @@ SIGNATURES = {
     "adgs_pixel_loss_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "adgs_pixel_loss": (C.c_int, [_P(PixelLossInputs), C.c_int32] + [C.c_void_p] * 8),
     "adgs_env_touched_bytes": (C.c_size_t, [C.c_int32]),
+    "adgs_env_tile_list_bytes": (C.c_size_t, [C.c_int32]),
     "adgs_env_forward": (C.c_int, [_P(EnvMap), C.c_int32, C.c_int32, C.c_float] + [C.c_void_p] * 6),
     "adgs_env_backward": (C.c_int, [_P(EnvMap), C.c_int32, C.c_int32, C.c_float] + [C.c_void_p] * 6),
     "adgs_env_adam_step": (C.c_int, [_P(EnvMap), C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]),

@@ -14,7 +14,8 @@
 // backward: recomputes the sample position (nothing is saved), d foreground = g, d opacity = -sum_c g_c bg_c,
 //           and scatters the texel gradients with RED.ADD into a PERSISTENT dense gradient buffer, marking the
 //           32x32-texel tiles it touches.
-// step    : Adam over the tiles that have EVER been touched, zeroing their gradient in the same pass. This is
+// step    : the touched-tile map is compacted into a list; Adam runs over the tiles that have EVER been touched
+//           (one CTA per tile), zeroing their gradient in the same pass. This is
 //           exactly dense Adam: a texel that never received a gradient has m = v = g = 0, so its update is
 //           0 / (0 + eps) = 0 and skipping it changes nothing; a tile touched once keeps being stepped (its
 //           moments decay like in the dense optimizer).
@@ -176,22 +177,41 @@ struct EnvAdamArgs {
     float w1, b2, w2, eps, bc2_sqrt, neg_step;
 };
 
-// One CTA per row of tiles; a warp takes the touched tiles of the row in turn (32 lanes = 32 texel columns).
+// Compaction of the touched-tile map: tile_list[0] = count, tile_list[1 + i] = tile id (any order).
+__global__ void __launch_bounds__(256) env_compact_kernel(const uint8_t* __restrict__ touched, int num_tiles,
+                                                          uint32_t* __restrict__ tile_list)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = t < num_tiles && touched[t] != 0;
+    const uint32_t mask = __ballot_sync(0xffffffffu, on);
+    if (mask == 0) return;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(tile_list, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (on) tile_list[1 + base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)t;
+}
+
+// One CTA per touched tile (grid-stride over the compacted list, whose length lives on the device): warp w
+// takes texel rows w, w+8, w+16, w+24 of the tile, lanes are the 32 columns -> 128-byte lines, and the
+// 4 rows x C channels of a thread are independent loads (memory-level parallelism instead of a serial walk).
 __global__ void __launch_bounds__(256) env_adam_kernel(const EnvAdamArgs a)
 {
     const int R = a.env.R;
     const int tiles = (R + kEnvTile - 1) / kEnvTile;
-    const int ty = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t RR = (size_t)R * R;
-    for (int tx = warp; tx < tiles; tx += 8) {
-        if (!a.env.touched[(size_t)ty * tiles + tx]) continue;
+    const uint32_t count = a.env.tile_list[0];
+    for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
+        const uint32_t t = a.env.tile_list[1 + i];
+        const int ty = (int)(t / tiles), tx = (int)(t - (uint32_t)ty * tiles);
         const int x = tx * kEnvTile + lane;
         if (x >= R) continue;
-        for (int c = 0; c < a.env.C; ++c) {
-            for (int r = 0; r < kEnvTile; ++r) {
-                const int y = ty * kEnvTile + r;
-                if (y >= R) break;
+#pragma unroll
+        for (int rr = 0; rr < kEnvTile / 8; ++rr) {
+            const int y = ty * kEnvTile + warp + 8 * rr;
+            if (y >= R) continue;
+            for (int c = 0; c < a.env.C; ++c) {
                 const size_t o = c * RR + (size_t)y * R + x;
                 const float g = a.env.grad[o];
                 float m = a.env.exp_avg[o], v = a.env.exp_avg_sq[o];
@@ -228,6 +248,11 @@ size_t adgs_env_touched_bytes(int32_t R)
     if (R <= 0) return 0;
     const size_t t = (size_t)((R + kEnvTile - 1) / kEnvTile);
     return t * t;
+}
+
+size_t adgs_env_tile_list_bytes(int32_t R)
+{
+    return (adgs_env_touched_bytes(R) + 1) * sizeof(uint32_t);
 }
 
 int adgs_env_forward(const adgs_env_map* env, int32_t H, int32_t W, float focal, const float* world_view_transform,
@@ -285,7 +310,7 @@ int adgs_env_adam_step(const adgs_env_map* env, double lr, double beta1, double 
     cudaStream_t stream = (cudaStream_t)stream_;
     int st = check_env(env);
     if (st) return st;
-    if (!env->grad || !env->exp_avg || !env->exp_avg_sq || !env->touched) return ADGS_ERR_ARG;
+    if (!env->grad || !env->exp_avg || !env->exp_avg_sq || !env->touched || !env->tile_list) return ADGS_ERR_ARG;
     if (step < 1 || !(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0)) return ADGS_ERR_ARG;
     const double bc1 = 1.0 - pow(beta1, (double)step);
     const double bc2 = 1.0 - pow(beta2, (double)step);
@@ -298,8 +323,12 @@ int adgs_env_adam_step(const adgs_env_map* env, double lr, double beta1, double 
     a.bc2_sqrt = (float)sqrt(bc2);
     a.neg_step = (float)(lr / bc1 * -1.0);
     const int tiles = (env->R + kEnvTile - 1) / kEnvTile;
-    env_adam_kernel<<<tiles, 256, 0, stream>>>(a);
-    count_launch(1);
+    const int num_tiles = tiles * tiles;
+    cudaMemsetAsync(env->tile_list, 0, sizeof(uint32_t), stream);
+    env_compact_kernel<<<(num_tiles + 255) / 256, 256, 0, stream>>>(env->touched, num_tiles, env->tile_list);
+    const int grid = min(num_tiles, device_info().sm_count * 8);
+    env_adam_kernel<<<grid, 256, 0, stream>>>(a);
+    count_launch(2);
     return check_stage("env adam", false, stream);
 }
 

@@ -129,7 +129,9 @@ class EnvironmentMap:
             z = lambda: torch.zeros_like(self.grid_map.detach())
             self._state = {"grad": z(), "exp_avg": z(), "exp_avg_sq": z(),
                            "touched": torch.zeros((lib.adgs_env_touched_bytes(self.resolution),), dtype=torch.uint8,
-                                                  device=self.grid_map.device)}
+                                                  device=self.grid_map.device),
+                           "tile_list": torch.zeros((lib.adgs_env_tile_list_bytes(self.resolution) // 4,),
+                                                    dtype=torch.int32, device=self.grid_map.device)}
         return self._state
 
     def _c_env(self, with_state):
@@ -140,6 +142,7 @@ class EnvironmentMap:
             s = self._ensure_state()
             e.grad, e.exp_avg, e.exp_avg_sq = s["grad"].data_ptr(), s["exp_avg"].data_ptr(), s["exp_avg_sq"].data_ptr()
             e.touched = s["touched"].data_ptr()
+            e.tile_list = s["tile_list"].data_ptr()
         return e
 
     @property

@@ -507,8 +507,10 @@ typedef struct adgs_env_map {
     float* exp_avg;       /* (1,C,R,R) (step) */
     float* exp_avg_sq;    /* (1,C,R,R) (step) */
     uint8_t* touched;     /* adgs_env_touched_bytes(R) (backward, step) */
+    uint32_t* tile_list;  /* adgs_env_tile_list_bytes(R): scratch of the step (compacted touched tiles) */
 } adgs_env_map;
 ADGS_API size_t adgs_env_touched_bytes(int32_t R);
+ADGS_API size_t adgs_env_tile_list_bytes(int32_t R);
 ADGS_API int adgs_env_forward(const adgs_env_map* env, int32_t H, int32_t W, float focal,
                               const float* world_view_transform, const float* foreground, const float* img_opacity,
                               float* background, float* rendered, adgs_stream_t stream);
