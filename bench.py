@@ -368,6 +368,7 @@ def run_ours(args):
         return out
 
     copy_stream = torch.cuda.Stream(device=device)
+    readback_stream = torch.cuda.Stream(device=device)
 
     # device -> host read of the step's metric: an asynchronous copy into pinned memory that the host
     # consumes two steps later (after the next two steps have been queued), the way a training loop logs its
@@ -387,9 +388,17 @@ def run_ours(args):
             metric_log.append(float(value_on_device.detach().item()))
             return
         buf = metric_ring[(len(metric_log) + len(metric_pending)) % 4]   # at most three reads in flight
-        buf.copy_(value_on_device.detach().reshape(1), non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(device))
+        # the 4-byte device-to-host copy runs on a side stream: in the compute stream it would sit between this
+        # step's last kernel and the next step's first one
+        val = value_on_device.detach().reshape(1)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(device))
+        with torch.cuda.stream(readback_stream):
+            readback_stream.wait_event(done)
+            buf.copy_(val, non_blocking=True)
+            val.record_stream(readback_stream)
+            ev = torch.cuda.Event()
+            ev.record(readback_stream)
         metric_pending.append((buf, ev))
         if len(metric_pending) > 2:
             consume_metric()
@@ -399,15 +408,19 @@ def run_ours(args):
             consume_metric()
 
     def e2e_step_exchange():
-        dcam = host_cam.to(device, non_blocking=True)
+        with torch.cuda.stream(copy_stream):
+            dcam = host_cam.to(device, non_blocking=True)
+            cam_ready = torch.cuda.Event()
+            cam_ready.record(copy_stream)
+            flat = host_cot.to(device, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        torch.cuda.current_stream(device).wait_event(cam_ready)
+        dcam.record_stream(torch.cuda.current_stream(device))
         views_ = list(all_views)
         views_[rank] = (cam._replace(world_view_transform=dcam[0:16].view(4, 4),
                                      full_proj_transform=dcam[16:32].view(4, 4), camera_center=dcam[32:35]),
                         all_views[rank][1])
-        with torch.cuda.stream(copy_stream):
-            flat = host_cot.to(device, non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(copy_stream)
         box = {}
 
         def cots(v, r):
@@ -424,13 +437,19 @@ def run_ours(args):
             return e2e_step_exchange()
         # host -> device: camera matrices first (needed by the forward), cotangent planes on a copy
         # stream so that the PCIe transfer overlaps the forward; the backward waits for them.
-        dcam = host_cam.to(device, non_blocking=True)
-        vc = cam._replace(world_view_transform=dcam[0:16].view(4, 4), full_proj_transform=dcam[16:32].view(4, 4),
-                          camera_center=dcam[32:35])
+        # Both copies go through the copy stream, camera first: a tiny camera copy issued on the compute stream
+        # would queue behind the 16.7 MB transfer on the host-to-device copy engine and stall the forward.
         with torch.cuda.stream(copy_stream):
+            dcam = host_cam.to(device, non_blocking=True)
+            cam_ready = torch.cuda.Event()
+            cam_ready.record(copy_stream)
             flat = host_cot.to(device, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(copy_stream)
+        torch.cuda.current_stream(device).wait_event(cam_ready)
+        dcam.record_stream(torch.cuda.current_stream(device))
+        vc = cam._replace(world_view_transform=dcam[0:16].view(4, 4), full_proj_transform=dcam[16:32].view(4, 4),
+                          camera_center=dcam[32:35])
         c = split_cot(flat)
         for p in params:
             p.grad = None
