@@ -224,6 +224,24 @@ class EnvMap(C.Structure):
                 ("exp_avg_sq", C.c_void_p), ("touched", C.c_void_p), ("tile_list", C.c_void_p)]
 
 
+class DensifyParams(C.Structure):
+    _fields_ = [("N_scene", C.c_int32), ("N_obj", C.c_int32), ("mode", C.c_int32), ("n_split", C.c_int32),
+                ("max_scene_grad", C.c_float), ("max_obj_grad", C.c_float), ("scene_split_size", C.c_float),
+                ("obj_split_size", C.c_float), ("min_opacity", C.c_float), ("prune_big", C.c_int32),
+                ("scene_big_size", C.c_float), ("obj_big_size", C.c_float), ("inv_split_scale", C.c_float),
+                ("_pad", C.c_int32)]
+
+
+class GatherSegment(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("planes", C.c_int32), ("width", C.c_int32),
+                ("src_rows", C.c_int32), ("dst_rows", C.c_int32), ("src_row0", C.c_int32), ("dst_row0", C.c_int32),
+                ("zero_new", C.c_int32), ("_pad", C.c_int32)]
+
+
+DENSIFY_AND_PRUNE, DENSIFY_PRUNE_ONLY = 0, 1
+DENSIFY_KIND_KEEP, DENSIFY_KIND_CLONE, DENSIFY_KIND_CHILD = 0, 1, 2
+GATHER_MAX_SEGMENTS = 40
+
 ADAM_MAX_SEGMENTS = 16
 ADAM_LR_UNIFORM, ADAM_LR_SPLIT, ADAM_LR_SH4 = 0, 1, 2
 
@@ -305,6 +323,16 @@ SIGNATURES = {
     "adgs_profile_end": (C.c_int, [C.c_void_p, C.c_void_p]),
     "adgs_knn_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "adgs_dist_cuda2": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adgs_densify_stats": (C.c_int, [C.c_int32] + [C.c_void_p] * 6),
+    "adgs_densify_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "adgs_densify_classify": (C.c_int, [_P(DensifyParams)] + [C.c_void_p] * 6 + [_P(C.c_int32), C.c_void_p]),
+    "adgs_densify_plan": (C.c_int, [_P(DensifyParams), C.c_void_p, _P(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adgs_densify_gather": (C.c_int, [_P(GatherSegment), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adgs_densify_split": (C.c_int, [C.c_int32, C.c_int32] + [C.c_void_p] * 7 + [C.c_int32, C.c_void_p, C.c_void_p,
+                                                                                C.c_void_p]),
+    "adgs_reset_opacity": (C.c_int, [C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "adgs_knn_points_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "adgs_knn_points": (C.c_int, [C.c_int32] * 4 + [C.c_void_p] * 6),
 }
 
 _lib = None

@@ -16,7 +16,9 @@ per-Gaussian blocks planar so that warps read whole 128-byte lines:
 (`_scene_xyz`, `_obj_xyz`, `xyz_deform_param (N_obj,3,Cx)`, ... gaussian_model.py:46-84,285-328),
 so checkpoints and parity tests speak the reference layout.
 
-Optimizer / densification / PLY code is out of scope.
+The optimizer (adgs_b200/optimizer.py), densification / pruning / near-index K-NN (adgs_b200/densify.py) and the
+PLY + deform.pth checkpoint formats (adgs_b200/checkpoint.py) hang off the same class under the reference's
+method names.
 """
 import ctypes as C
 import math
@@ -265,6 +267,36 @@ class GaussianModel(nn.Module):
     def update_learning_rate(self, iteration):
         from .optimizer import update_learning_rate
         update_learning_rate(self, iteration)
+
+    # ---- densification (scene/gaussian_model.py:463-467, 560-867), see adgs_b200/densify.py ----------------
+    def add_densification_stats(self, render_pkg, update_max_radii=True):
+        from .densify import add_densification_stats
+        add_densification_stats(self, render_pkg, update_max_radii=update_max_radii)
+
+    def densify_and_prune(self, max_scene_grad, max_obj_grad, min_opacity, prune_big_points, **kw):
+        from .densify import densify_and_prune
+        return densify_and_prune(self, max_scene_grad, max_obj_grad, min_opacity, prune_big_points, **kw)
+
+    def prune_points(self, scene_mask, obj_mask):
+        from .densify import prune_points
+        return prune_points(self, scene_mask, obj_mask)
+
+    def reset_opacity(self):
+        from .densify import reset_opacity
+        reset_opacity(self)
+
+    def set_obj_near_idx(self, K=None):
+        from .densify import set_obj_near_idx
+        set_obj_near_idx(self, K)
+
+    # ---- checkpoints (scene/gaussian_model.py:415-543), see adgs_b200/checkpoint.py -------------------------
+    def save_ply(self, path):
+        from .checkpoint import save_ply
+        save_ply(self, path)
+
+    def load_ply(self, path, device="cuda"):
+        from .checkpoint import load_ply
+        load_ply(self, path, device=device)
 
     def _note_active_columns(self, tb):
         """Control-point columns the backward of this render writes (window-aware optimizer step)."""

@@ -230,3 +230,18 @@ def get_flow_loss(img_flow, flow_pkg, img_opacity=None, dist=1e-3):
     returns the python float 0.0) -- and never synchronises with the host."""
     return _PixelLosses.apply(None, None, img_opacity, img_flow, dict(flow_pkg=flow_pkg, flow_dist=dist),
                               dict(flow=1.0))[4]
+
+
+def near_reg_loss(model):
+    """train.py:101-103: mean over anchors and axes of the variance (over the K near neighbours, unbiased) of the
+    position control points, summed over the control-point axis -- on the planar (Cx, 3, N_obj) array:
+    `xyz_deform_param[obj_near_idx]` (P,K,3,C) -> var(dim=1).sum(-1).mean()  ==  xyz_deform[:, :, idx] (C,3,P,K)
+    -> var(dim=-1).sum(0).mean(). Plain torch on the device (a gather + reduction, differentiable);
+    `obj_near_idx` comes from adgs_b200.densify.set_obj_near_idx."""
+    idx = model.obj_near_idx
+    return torch.mean(torch.sum(torch.var(model.xyz_deform[:, :, idx], dim=-1), dim=0))
+
+
+def near_sigma_reg_loss(model):
+    """train.py:108-110: `gs_time_sigma[obj_near_idx]` (P,K,2) -> var(dim=1).sum(-1).mean()."""
+    return torch.mean(torch.sum(torch.var(model.gs_time_sigma[model.obj_near_idx], dim=1), dim=-1))

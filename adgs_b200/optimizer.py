@@ -62,7 +62,9 @@ class FusedAdam:
         self.betas = (float(betas[0]), float(betas[1]))
         self.eps = float(eps)
         self.window_aware = bool(window_aware)
-        self.step_count = 0
+        # torch.optim.Adam keeps one step count per parameter and skips parameters without a gradient (the
+        # iteration after a densification: every per-Gaussian tensor is new, only deform_background steps)
+        self.step_counts = {k: 0 for k in PARAM_NAMES}
         lrs = dict(lrs or {})
         unknown = set(lrs) - set(GROUP_NAMES)
         if unknown:
@@ -106,18 +108,28 @@ class FusedAdam:
                              f"(the reference gives them the same value, scene/gaussian_model.py:346-370)")
         return self._lr(a)
 
+    @property
+    def step_count(self):
+        return max(self.step_counts.values())
+
+    @step_count.setter
+    def step_count(self, value):
+        self.step_counts = {k: int(value) for k in PARAM_NAMES}
+
     def _segments(self):
+        """[(array name, adgs_adam_segment)] of the arrays that have a gradient."""
         m = self.model
         n, ns, no = m.n_scene + m.n_obj, m.n_scene, m.n_obj
-        active = m.active_columns() if self.window_aware else None
+        need_active = self.window_aware and (m.xyz_deform.grad is not None or m.rot_deform.grad is not None)
+        active = m.active_columns() if need_active else None
         segs = []
 
         def add(key, lr_a, lr_b=0.0, rule=L.ADAM_LR_UNIFORM, split=0, plane=0, cols=None):
             p = getattr(m, key)
             if p.numel() == 0:
                 return
-            if p.grad is None:
-                raise RuntimeError(f"FusedAdam.step(): parameter {key} has no gradient")
+            if p.grad is None:      # torch.optim.Adam skips it
+                return
             st = self.state[key]
             if not (p.is_contiguous() and p.grad.is_contiguous()):
                 raise RuntimeError(f"FusedAdam.step(): {key} and its gradient must be contiguous")
@@ -130,7 +142,7 @@ class FusedAdam:
                 for c in cols:
                     bits[c >> 6] |= 1 << (c & 63)
                 s.active[0], s.active[1] = bits
-            segs.append(s)
+            segs.append((key, s))
 
         add("xyz", self._lr("scene_xyz"), self._lr("obj_xyz"), L.ADAM_LR_SPLIT, split=3 * ns)
         add("scaling", self._check_shared("scene_scaling", "obj_scaling"))
@@ -149,15 +161,20 @@ class FusedAdam:
     def step(self):
         lib = L.load()
         segs = self._segments()
-        self.step_count += 1
         if not segs:
             return
         dev = self.model.xyz.device
-        arr = (L.AdamSegment * len(segs))(*segs)
-        with torch.cuda.device(dev):
-            st = lib.adgs_adam_step(arr, len(segs), self.betas[0], self.betas[1], self.eps, self.step_count,
-                                    torch.cuda.current_stream(dev).cuda_stream)
-        L.check(st, "adam_step")
+        by_step = {}
+        for key, s in segs:
+            self.step_counts[key] += 1
+            by_step.setdefault(self.step_counts[key], []).append(s)
+        # one launch; a second one only while deform_background is ahead of the per-Gaussian arrays
+        for step, group in by_step.items():
+            arr = (L.AdamSegment * len(group))(*group)
+            with torch.cuda.device(dev):
+                st = lib.adgs_adam_step(arr, len(group), self.betas[0], self.betas[1], self.eps, step,
+                                        torch.cuda.current_stream(dev).cuda_stream)
+            L.check(st, "adam_step")
         if self.window_aware:
             self.model.reset_active_columns()
 
@@ -185,7 +202,7 @@ class FusedAdam:
             planar = self.model.planar_layout({name: d[which] for name, d in ref_state.items()})
             for k in PARAM_NAMES:
                 self.state[k][which].copy_(planar[k])
-        self.step_count = int(step)
+        self.step_count = int(step)   # all arrays
 
 
 def training_setup(model, training_args, window_aware=False):
@@ -214,6 +231,14 @@ def training_setup(model, training_args, window_aware=False):
     model.obj_xyz_scheduler_args = mk(model.object_extent, a.obj_position_lr_scale)
     model.scene_xyz_scheduler_args = mk(model.cameras_extent, a.scene_position_lr_scale)
     model.deform_scheduler_args = mk(model.scene_extent, a.position_deform_lr_scale)
+    # densification statistics and the near-index table (gaussian_model.py:340-341, 395-397)
+    from .densify import set_obj_near_idx, setup_statistics
+    setup_statistics(model)
+    lam = lambda k: float(getattr(a, k, 0.0) or 0.0)
+    model.use_near_idx = lam("lambda_reg") > 0.0 or (lam("lambda_sigma") > 0.0 and lam("lambda_sigma_reg") > 0.0)
+    model.near_num = int(getattr(a, "near_num", 0) or 0)
+    if model.use_near_idx and model.xyz.is_cuda:
+        set_obj_near_idx(model)
     return model.optimizer
 
 

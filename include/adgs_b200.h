@@ -540,6 +540,98 @@ ADGS_API size_t adgs_knn_workspace_bytes(int32_t P);
 ADGS_API int adgs_dist_cuda2(int32_t P, const float* points, float* mean_dist2, char* workspace,
                     adgs_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Densification / pruning over the planar storage of adgs_model.
+ * Replaces GaussianModel.densify_and_prune / densify_and_clone / densify_and_split / prune_points /
+ * _prune_optimizer / cat_tensors_to_optimizer / densification_postfix / add_densification_stats /
+ * reset_opacity (scene/gaussian_model.py:463-467, 547-861, 863-867) and the max_radii2D update of
+ * train.py:151. Rows are ordered [scene ; object] like adgs_model; the result of clone -> split -> prune
+ * is, per partition, [originals neither split nor pruned] ++ [clones] ++ [children copy 0] ++ ...
+ * ++ [children copy n_split-1], each in source order -- the order the reference's torch.cat / mask
+ * chain produces.
+ *
+ *   adgs_densify_stats     visible (radii > 0) rows: max_radii2D = max(max_radii2D, radii),
+ *                          xyz_gradient_accum += |grad_means2D[:, :2]|, denom += 1. accum/denom or
+ *                          max_radii2D may be null (skipped).
+ *   adgs_densify_classify  per-row decisions + counts. host_totals8 (HOST memory, may be null = no
+ *                          synchronisation) receives, per partition p in {scene, object}:
+ *                          [4p+0] originals kept, [4p+1] clones, [4p+2] split sources whose children
+ *                          survive, [4p+3] split sources selected (= rows of unit normals to draw / n_split).
+ *                          New row count of partition p = [4p+0] + [4p+1] + n_split * [4p+2].
+ *                          mode ADGS_DENSIFY_PRUNE_ONLY: keep the rows whose prune_mask byte is 0
+ *                          (prune_points with explicit masks); the other inputs may be null.
+ *   adgs_densify_plan      src[d] = source row of output row d; tag[d] = kind | (sample row << 2).
+ *   adgs_densify_gather    ONE launch over up to ADGS_GATHER_MAX_SEGMENTS arrays: dst[plane][r][0..width)
+ *                          = src[plane][src[dst_row0 + r] - src_row0][0..width), or zeros when zero_new is
+ *                          set and the row is a clone / child (Adam moments of new points,
+ *                          cat_tensors_to_optimizer).
+ *   adgs_densify_split     rows tagged CHILD: new_xyz = R(q/|q|) (z * exp(scaling)) + xyz,
+ *                          new_scaling = log(exp(scaling) / (0.8 n_split)); z_scene / z_obj are the unit
+ *                          normals (n_split * selected, 3), i.e. torch.normal(0, stds) = randn * stds.
+ *   adgs_reset_opacity     opacity = inverse_sigmoid(min(sigmoid(opacity), cap)); moments zeroed.
+ * Thresholds are floats: the reference compares float tensors with python scalars, which torch
+ * evaluates in float.
+ * ---------------------------------------------------------------------------------------- */
+enum { ADGS_DENSIFY_AND_PRUNE = 0, ADGS_DENSIFY_PRUNE_ONLY = 1 };
+enum { ADGS_DENSIFY_KIND_KEEP = 0, ADGS_DENSIFY_KIND_CLONE = 1, ADGS_DENSIFY_KIND_CHILD = 2 };
+typedef struct adgs_densify_params {
+    int32_t N_scene, N_obj;
+    int32_t mode;            /* ADGS_DENSIFY_AND_PRUNE | ADGS_DENSIFY_PRUNE_ONLY */
+    int32_t n_split;         /* N of densify_and_split (2) */
+    float max_scene_grad;    /* densify_scene_grad_threshold */
+    float max_obj_grad;      /* densify_obj_grad_threshold */
+    float scene_split_size;  /* scene_extent * percent_dense */
+    float obj_split_size;    /* object_extent * percent_dense */
+    float min_opacity;       /* 0.005 */
+    int32_t prune_big;       /* prune_big_points */
+    float scene_big_size;    /* scene_extent * 0.05 */
+    float obj_big_size;      /* object_extent * 0.1 */
+    float inv_split_scale;   /* filled by the library: 1 / (float)(0.8 n_split) */
+    int32_t _pad;
+} adgs_densify_params;
+
+ADGS_API int adgs_densify_stats(int32_t N, const float* grad_means2D, const int32_t* radii,
+                                float* xyz_gradient_accum, float* denom, float* max_radii2D, adgs_stream_t stream);
+ADGS_API size_t adgs_densify_workspace_bytes(int32_t N_scene, int32_t N_obj);
+ADGS_API int adgs_densify_classify(const adgs_densify_params* params, const float* xyz_gradient_accum,
+                                   const float* denom, const float* scaling, const float* opacity,
+                                   const uint8_t* prune_mask, char* workspace, int32_t* host_totals8,
+                                   adgs_stream_t stream);
+ADGS_API int adgs_densify_plan(const adgs_densify_params* params, const char* workspace, const int32_t* host_totals8,
+                               int32_t* src, int32_t* tag, adgs_stream_t stream);
+
+#define ADGS_GATHER_MAX_SEGMENTS 40
+typedef struct adgs_gather_segment {
+    const float* src;  /* (planes, src_rows, width) */
+    float* dst;        /* (planes, dst_rows, width) */
+    int32_t planes;
+    int32_t width;     /* 1..4 floats per row and plane */
+    int32_t src_rows;
+    int32_t dst_rows;
+    int32_t src_row0;  /* global index of this array's first row: 0, or the OLD N_scene for object-only arrays */
+    int32_t dst_row0;  /* 0, or the NEW N_scene */
+    int32_t zero_new;  /* 1: rows that are clones / children are written as zeros */
+    int32_t _pad;
+} adgs_gather_segment;
+ADGS_API int adgs_densify_gather(const adgs_gather_segment* segments, int32_t num_segments, const int32_t* src,
+                                 const int32_t* tag, adgs_stream_t stream);
+ADGS_API int adgs_densify_split(int32_t n_dst, int32_t n_scene_dst, const int32_t* src, const int32_t* tag,
+                                const float* xyz, const float* scaling, const float* rotation, const float* z_scene,
+                                const float* z_obj, int32_t n_split, float* new_xyz, float* new_scaling,
+                                adgs_stream_t stream);
+ADGS_API int adgs_reset_opacity(int32_t N, float cap, float* opacity, float* exp_avg, float* exp_avg_sq,
+                                adgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K nearest neighbours: replaces pytorch3d.ops.knn_points(anchor[None], xyz[None], K).idx of
+ * GaussianModel.set_obj_near_idx (scene/gaussian_model.py:825-833). anchors (A,D), points (P,D),
+ * D = 3 or 4, K <= 32 and K <= P. idx (A,K) int64 ascending by squared distance, ties by smaller index;
+ * dists (A,K) squared distances, may be null.
+ * ---------------------------------------------------------------------------------------- */
+ADGS_API size_t adgs_knn_points_workspace_bytes(int32_t A, int32_t P, int32_t K);
+ADGS_API int adgs_knn_points(int32_t A, int32_t P, int32_t D, int32_t K, const float* anchors, const float* points,
+                             int64_t* idx, float* dists, char* workspace, adgs_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

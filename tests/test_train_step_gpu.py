@@ -59,3 +59,48 @@ def test_training_iterations_reduce_the_loss(window_aware):
     assert torch.isfinite(losses).all()
     assert losses[-5:].mean() < 0.8 * losses[:5].mean(), losses.tolist()
     assert model.optimizer.step_count == 40
+
+
+@pytest.mark.parametrize("window_aware", [False, True])
+def test_training_with_densification_and_near_regularisers(window_aware):
+    """train.py:74-167 including the densification block (:149-160) and, in the dense optimizer mode, the
+    near-index regularisers (:101-110): the Gaussian set changes every 10 iterations, the optimizer state follows
+    it, deform_background runs one Adam step ahead of the per-Gaussian arrays after each densification (torch's
+    per-parameter step counts), and the loss stays finite."""
+    pipe = SimpleNamespace(inv_depth=True, debug=False, sync_free=True)
+    target_model, cam, W, H = _build(seed=2)
+    with torch.no_grad():
+        target_model.sh4.mul_(0.3).add_(0.2)
+        tgt = render(_view(cam, 0.4), target_model, None, pipe, render_objmask=True)
+    targets = dict(original_image=tgt["render"].clamp(0, 1).clone(), depth=tgt["depth"].clone(),
+                   semantic=(tgt["img_semantic"][0] > 0.5).float(), sky=(tgt["img_opacity"] < 0.05).float())
+    model, _, _, _ = _build(seed=2)
+    model.scene_extent = 20.0
+    args = SimpleNamespace(**vars(ARGS), lambda_reg=0.0 if window_aware else 0.5, lambda_sigma=0.01,
+                           lambda_sigma_reg=0.0 if window_aware else 0.5, near_num=8)
+    opt = SimpleNamespace(**vars(OPT), lambda_reg=args.lambda_reg, lambda_sigma_reg=args.lambda_sigma_reg,
+                          densify_until_iter=26, densify_from_iter=0, densification_interval=10,
+                          opacity_reset_interval=15, densify_scene_grad_threshold=1e-7, densify_obj_grad_threshold=1e-7,
+                          near_idx_reset_interval=5)
+    model.training_setup(args, window_aware=window_aware)
+    assert model.use_near_idx == (not window_aware)
+    if not window_aware:
+        assert model.obj_near_idx.shape == (2000 // 8, 8)
+    view = _view(cam, 0.4, **targets)
+    counts, losses = [], []
+    for it in range(1, 31):
+        logs, pkg = training_iteration(model, view, opt, pipe, it, frame_gap=1.0 / 96, densify=opt)
+        counts.append(model.get_pts_num)
+        losses.append(logs["total_loss"])
+        if not window_aware:
+            assert logs["reg_loss"] is not None and logs["reg_sigma_loss"] is not None
+    assert torch.isfinite(torch.stack(losses)).all()
+    assert counts[9] != counts[8] and counts[19] != counts[18]      # densified at iterations 10 and 20
+    assert counts[29] == counts[19]                                 # densify_until_iter
+    sc = model.optimizer.step_counts
+    assert sc["background_deform"] == 30 and sc["xyz"] == 28 and sc["rot_deform"] == 28
+    assert model.xyz_gradient_accum.shape[0] == model.get_pts_num
+    assert model.optimizer.state["sh4"]["exp_avg"].shape == model.sh4.shape
+    if not window_aware:
+        assert int(model.obj_near_idx.max()) < model.n_obj
+    assert float(torch.sigmoid(model.opacity).max()) <= 1.0
