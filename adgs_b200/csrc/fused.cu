@@ -1220,54 +1220,86 @@ int run_blend_backward(const adgs_camera* cam, int P, int render_objmask, bool h
     return check_stage("blend backward", cam->debug != 0, stream);
 }
 
+// Dense-gradient semantics: everything outside the active control-point columns is zero. The kernels write
+// every active plane in full, so only the complement is memset (plane = all objects of a column); when
+// accumulating over the views of a batch only the first view fills. `fill_stream` may be a side stream: the
+// memsets are pure HBM writes and overlap the issue-bound blend backward (adgs_render_backward).
+void issue_gradient_fills(const adgs_model* model, const adgs_time_basis* basis, const adgs_model* grads,
+                          int accumulate, float* bg_scratch, cudaStream_t stream)
+{
+    const int No = model->N_obj;
+    cudaMemsetAsync(bg_scratch, 0, 32 * sizeof(float), stream);
+    auto zero_inactive = [&](float* base, const adgs_lin_basis& lin, int quat_start, int quat_count,
+                             size_t plane_floats) {
+        const int C = lin.n_cols;
+        if (!base || C <= 0 || No <= 0) return;
+        bool active[2 * ADGS_MAX_TERMS + 64];
+        const int cap = (int)(sizeof(active) / sizeof(active[0]));
+        if (C > cap) {
+            cudaMemsetAsync(base, 0, (size_t)C * plane_floats * sizeof(float), stream);
+            return;
+        }
+        for (int c = 0; c < C; ++c) active[c] = false;
+        for (int t = 0; t < lin.n; ++t) active[lin.col[t]] = true;
+        for (int i = 0; i < quat_count; ++i)
+            if (quat_start + i < C) active[quat_start + i] = true;
+        int c = 0;
+        while (c < C) {
+            if (active[c]) {
+                ++c;
+                continue;
+            }
+            int e = c;
+            while (e < C && !active[e]) ++e;
+            cudaMemsetAsync(base + (size_t)c * plane_floats, 0, (size_t)(e - c) * plane_floats * sizeof(float), stream);
+            c = e;
+        }
+    };
+    if (!accumulate && !basis->sparse_grads) {
+        zero_inactive(grads->xyz_deform, basis->xyz, 0, 0, (size_t)3 * No);
+        zero_inactive(grads->rot_deform, basis->rotation, basis->quat.start,
+                      basis->quat.n_ctrl ? basis->quat.k + 1 : 0, (size_t)4 * No);
+    }
+}
+
+// One non-blocking side stream + fork / join events per device, created on first use.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok = false;
+};
+
+SideStream& side_stream()
+{
+    static SideStream table[64];
+    static bool tried[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    SideStream& s = table[dev];
+    if (!tried[dev]) {
+        tried[dev] = true;
+        s.ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+               cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess;
+        if (!s.ok) cudaGetLastError();
+    }
+    return s;
+}
+
 int run_per_gaussian_backward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
                               const int32_t* radii, const float* cov3D, const uint8_t* clamped, const float4* saved,
                               const float* grad_record, const adgs_model* grads, int accumulate, float* dL_dmeans2D,
-                              float4* dq_scratch, float* bg_scratch, cudaStream_t stream)
+                              float4* dq_scratch, float* bg_scratch, cudaStream_t stream, bool fills_done = false)
 {
     const bool debug = cam->debug != 0;
     const int N = model->N_scene + model->N_obj;
     const int No = model->N_obj;
     int st;
     if (basis->sparse_grads && accumulate) return ADGS_ERR_ARG;  // unwritten planes cannot be accumulated into
-    {
-        // dense-gradient semantics: everything outside the active columns is zero. The kernels write
-        // every active plane in full, so only the complement is memset (plane = all objects of a
-        // column); when accumulating over the views of a batch only the first view fills.
+    if (!fills_done) {
         StageScope sc(kStageFills, stream);
-        cudaMemsetAsync(bg_scratch, 0, 32 * sizeof(float), stream);
-        auto zero_inactive = [&](float* base, const adgs_lin_basis& lin, int quat_start, int quat_count,
-                                 size_t plane_floats) {
-            const int C = lin.n_cols;
-            if (!base || C <= 0 || No <= 0) return;
-            bool active[2 * ADGS_MAX_TERMS + 64];
-            const int cap = (int)(sizeof(active) / sizeof(active[0]));
-            if (C > cap) {
-                cudaMemsetAsync(base, 0, (size_t)C * plane_floats * sizeof(float), stream);
-                return;
-            }
-            for (int c = 0; c < C; ++c) active[c] = false;
-            for (int t = 0; t < lin.n; ++t) active[lin.col[t]] = true;
-            for (int i = 0; i < quat_count; ++i)
-                if (quat_start + i < C) active[quat_start + i] = true;
-            int c = 0;
-            while (c < C) {
-                if (active[c]) {
-                    ++c;
-                    continue;
-                }
-                int e = c;
-                while (e < C && !active[e]) ++e;
-                cudaMemsetAsync(base + (size_t)c * plane_floats, 0, (size_t)(e - c) * plane_floats * sizeof(float),
-                                stream);
-                c = e;
-            }
-        };
-        if (!accumulate && !basis->sparse_grads) {
-            zero_inactive(grads->xyz_deform, basis->xyz, 0, 0, (size_t)3 * No);
-            zero_inactive(grads->rot_deform, basis->rotation, basis->quat.start,
-                          basis->quat.n_ctrl ? basis->quat.k + 1 : 0, (size_t)4 * No);
-        }
+        issue_gradient_fills(model, basis, grads, accumulate, bg_scratch, stream);
     }
     FusedBwdArgs a;
     memset(&a, 0, sizeof(a));
@@ -1421,12 +1453,28 @@ int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const 
     carve(sc, bg_scratch, 32);
     float4* saved4 = nullptr;
     carve(svc, saved4, (size_t)N * 3);
-    if ((st = run_blend_backward(cam, N, render_objmask, basis->has_flow != 0,
-                                 reinterpret_cast<const float4*>(gs.record), bs, is, capacity, img_opacity, dpix,
-                                 grad_record, gs.counters, stream)))
-        return st;
+    // The zero-fill of the inactive control-point planes (~260 MB at 250 k object Gaussians) is pure HBM write
+    // traffic and the blend backward is issue-bound: run the fill on a side stream underneath it
+    // (fork / join with events; ADGS_TUNE_FILL=1 keeps everything on the caller's stream).
+    static const int fill_variant = tune_variant("ADGS_TUNE_FILL", 0);
+    bool fills_done = false;
+    SideStream* side = nullptr;
+    if (fill_variant == 0 && !basis->sparse_grads && model->N_obj > 0 && !cam->debug) {
+        side = &side_stream();
+        if (side->ok && cudaEventRecord(side->fork, stream) == cudaSuccess &&
+            cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess) {
+            issue_gradient_fills(model, basis, grads, 0, bg_scratch, side->stream);
+            fills_done = cudaEventRecord(side->join, side->stream) == cudaSuccess;
+        }
+        if (!fills_done) cudaGetLastError();
+    }
+    st = run_blend_backward(cam, N, render_objmask, basis->has_flow != 0, reinterpret_cast<const float4*>(gs.record),
+                            bs, is, capacity, img_opacity, dpix, grad_record, gs.counters, stream);
+    if (fills_done && cudaStreamWaitEvent(stream, side->join, 0) != cudaSuccess)   // always join, even on error
+        return record_cuda_error(cudaGetLastError(), "gradient fill join");
+    if (st) return st;
     return run_per_gaussian_backward(cam, model, basis, radii, gs.cov3D, gs.clamped, saved4, grad_record, grads, 0,
-                                     dL_dmeans2D, dq_scratch, bg_scratch, stream);
+                                     dL_dmeans2D, dq_scratch, bg_scratch, stream, fills_done);
 }
 
 /* ---- splat exchange: Gaussian-sharded front end / back end, view-sharded blend ------------------------ */

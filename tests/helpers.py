@@ -22,9 +22,9 @@ def has_cuda():
 
 def make_case(n=5000, W=160, H=96, seed=0, sh_degree=3, inv_depth=True, flow=True, D_S=1, bg=(0.0, 0.0, 0.0),
               median_radius_px=4.0, device="cuda", colors_precomp=False, cov3D_precomp=False, scale_modifier=1.0,
-              yaw_deg=0.0):
+              yaw_deg=0.0, cluster=None):
     cam = scenes.make_camera(W, H, 90.0, yaw_deg=yaw_deg, device=device)
-    cloud = scenes.random_cloud(n, cam, seed=seed, median_radius_px=median_radius_px)
+    cloud = scenes.random_cloud(n, cam, seed=seed, median_radius_px=median_radius_px, cluster=cluster)
     inp = scenes.activated_inputs(cloud, device=device)
     g = torch.Generator(device="cpu").manual_seed(seed + 1)
     e = torch.Tensor([])

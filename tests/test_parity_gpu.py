@@ -44,6 +44,10 @@ CASES = {
     "medium": dict(n=200_000, W=640, H=360, seed=9),
     # BASELINE.json configs[1] at full size, against the unmodified reference kernels
     "kitti_full": dict(n=1_000_000, W=1242, H=375, seed=10, median_radius_px=3.0),
+    # BASELINE.json configs[2] (one camera of the Waymo-shaped rig, 45 sort bits) and configs[4] (stress: median
+    # radius 12 px, half of the Gaussians inside 5 % of the screen, 46 sort bits, ~10^8 instances) at full size
+    "waymo_full": dict(n=3_000_000, W=1600, H=1066, seed=11, median_radius_px=3.0, yaw_deg=45.0),
+    "stress_full": dict(n=10_000_000, W=1920, H=1280, seed=12, median_radius_px=12.0, cluster=(0.5, 0.05)),
 }
 
 
