@@ -214,6 +214,54 @@ class GaussianModel(nn.Module):
         m.active_sh_degree = sh_degree
         return m
 
+    @classmethod
+    def create_from_pcd(cls, pcd, scene_extent, cameras_extent, frame_gap, default_order_downsample_ratio,
+                        sh_degree=3, order_args=None, use_time_mask=True, device="cuda"):
+        """GaussianModel.create_from_pcd (scene/gaussian_model.py:255-333): initial Gaussians from a point cloud
+        with `.points (P,3)`, `.colors (P,3)` in [0,1], `.time (P,1)`, `.obj_id (P,1)` (utils/graphics_utils.py:17-22).
+        Scales from the mean squared distance to the 3 nearest neighbours (distCUDA2 -> adgs_dist_cuda2), identity
+        rotations, opacity 0.1, DC colour = RGB2SH, deformation parameters U(-1,1) * 1e-5 drawn with torch.rand in
+        the reference's order (xyz, rotation, shs, background), gs_time_sigma = log(frame_gap)."""
+        from .simple_knn import distCUDA2
+        order_args = set_default_param_order(order_args if order_args is not None else DEFAULT_ORDER_ARGS,
+                                             int(1.0 / frame_gap), default_order_downsample_ratio)
+        pts = torch.tensor(np.asarray(pcd.points)).float().to(device)
+        n = pts.shape[0]
+        fused_color = (torch.tensor(np.asarray(pcd.colors)).float().to(device) - 0.5) / 0.28209479177387814  # RGB2SH
+        shs = torch.zeros((n, 3, (sh_degree + 1) ** 2), dtype=torch.float32, device=device)
+        shs[:, :3, 0] = fused_color
+        shs = shs.transpose(1, 2)                                                     # (P,16,3)
+        dist2 = torch.clamp_min(distCUDA2(pts), 0.0000001)
+        scales = torch.log(torch.sqrt(dist2))[..., None].repeat(1, 3)
+        rots = torch.zeros((n, 4), device=device)
+        rots[:, 0] = 1.0
+        opac = torch.full((n, 1), math.log(0.1 / 0.9), dtype=torch.float32, device=device)  # inverse_sigmoid(0.1)
+        scene_mask = torch.tensor(np.asarray(pcd.obj_id)[..., 0] <= 0.5, dtype=torch.bool, device=device)
+        obj_mask = torch.logical_not(scene_mask)
+        no = int(obj_mask.sum())
+        U = lambda *shape: (torch.rand(shape, device=device, dtype=torch.float32) * 2.0 - 1.0) * 1e-5
+        xyz_deform = U(no, 3, get_param_num(order_args['xyz']))
+        rot_deform = U(no, 4, get_param_num(order_args['rotation']))
+        shs_deform = U(n, 3, get_param_num(order_args['shs']))
+        bg_deform = U(1, 3, get_param_num(order_args['background']))
+        ref = dict(
+            scene_xyz=pts[scene_mask], obj_xyz=pts[obj_mask],
+            scene_shs_dc=shs[scene_mask, 0:1], obj_shs_dc=shs[obj_mask, 0:1],
+            scene_shs_rest=shs[scene_mask, 1:], obj_shs_rest=shs[obj_mask, 1:],
+            scene_scaling=scales[scene_mask], obj_scaling=scales[obj_mask],
+            scene_rotation=rots[scene_mask], obj_rotation=rots[obj_mask],
+            scene_opacity=opac[scene_mask], obj_opacity=opac[obj_mask],
+            xyz_deform_param=xyz_deform, rotation_deform_param=rot_deform,
+            shs_deform_param_scene=shs_deform[scene_mask], shs_deform_param_obj=shs_deform[obj_mask],
+            background_deform_param=bg_deform,
+            gs_time=torch.tensor(np.asarray(pcd.time), device=device, dtype=torch.float32)[obj_mask],
+            gs_time_sigma=torch.full((no, 2), float(np.log(frame_gap)), dtype=torch.float32, device=device))
+        m = cls.from_reference(ref, order_args, sh_degree=sh_degree, use_time_mask=use_time_mask, device=device)
+        m.active_sh_degree = 0
+        m.scene_extent, m.cameras_extent, m.object_extent, m.frame_gap = scene_extent, cameras_extent, 10.0, frame_gap
+        m.max_radii2D = torch.zeros((n,), device=device)
+        return m
+
     def reference_layout(self, t: dict) -> dict:
         """Planar arrays (keys = PARAM_NAMES, e.g. parameters, gradients or optimizer moments) -> the
         reference's tensors by attribute name (inverse of planar_layout)."""

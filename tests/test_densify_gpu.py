@@ -309,3 +309,34 @@ def test_knn_points_large_timing():
     torch.testing.assert_close(d[sel], wd, rtol=1e-5, atol=1e-6)
     print(f"knn_points 31k x 250k, K=8: {ms:.2f} ms ({31_250 * 250_000 / ms / 1e6:.1f} G pairs/s)")
     assert ms < 100.0
+
+
+def test_create_from_pcd_mirrors_reference():
+    """scene/gaussian_model.py:255-333 on the planar storage: scales from distCUDA2, DC colour = RGB2SH, opacity 0.1,
+    identity rotations, scene / object split by obj_id, deformation parameters U(-1,1)*1e-5, sigma = log(frame_gap)."""
+    from adgs_b200.simple_knn import distCUDA2
+    rng = np.random.default_rng(0)
+    P = 5000
+    pcd = SimpleNamespace(points=rng.standard_normal((P, 3)) * 10, colors=rng.random((P, 3)),
+                          time=rng.random((P, 1)), obj_id=(rng.random((P, 1)) < 0.3).astype(np.float64))
+    torch.manual_seed(0)
+    m = GaussianModel.create_from_pcd(pcd, scene_extent=30.0, cameras_extent=8.0, frame_gap=1.0 / 96,
+                                      default_order_downsample_ratio=3)
+    obj = pcd.obj_id[:, 0] > 0.5
+    assert (m.n_scene, m.n_obj) == (int((~obj).sum()), int(obj.sum()))
+    assert m.order_args["xyz"] == [32, 5, 0, 6, 0, 0] and m.order_args["rotation"] == [0, 0, 0, 0, 32, 1]
+    ref = m.to_reference()
+    pts = torch.tensor(pcd.points).float().cuda()
+    d2 = torch.clamp_min(distCUDA2(pts), 1e-7)
+    want_scale = torch.log(torch.sqrt(d2))[:, None].repeat(1, 3)
+    assert torch.equal(ref["scene_scaling"], want_scale[torch.from_numpy(~obj).cuda()])
+    assert torch.equal(ref["obj_xyz"], pts[torch.from_numpy(obj).cuda()])
+    want_dc = (torch.tensor(pcd.colors).float().cuda() - 0.5) / 0.28209479177387814
+    torch.testing.assert_close(ref["scene_shs_dc"][:, 0], want_dc[torch.from_numpy(~obj).cuda()])
+    assert not bool(ref["obj_shs_rest"].any())
+    torch.testing.assert_close(torch.sigmoid(ref["obj_opacity"]), torch.full_like(ref["obj_opacity"], 0.1))
+    assert bool((ref["scene_rotation"] == torch.tensor([1.0, 0, 0, 0]).cuda()).all())
+    assert ref["xyz_deform_param"].shape == (m.n_obj, 3, 44) and float(ref["xyz_deform_param"].abs().max()) <= 1e-5
+    torch.testing.assert_close(ref["gs_time"][:, 0], torch.tensor(pcd.time[obj, 0]).float().cuda())
+    assert torch.allclose(ref["gs_time_sigma"], torch.tensor(float(np.log(1.0 / 96))).cuda())
+    assert m.active_sh_degree == 0 and m.max_radii2D.shape == (P,)
