@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(TPB, MINB) fused_forward_kernel(const __grid_c
     dc[1] = shq0.y;
     dc[2] = shq0.z;
     if (tb.shs.n) {
-        // (3,Cs) block in float4 chunks; gather the term columns
         const int Cs = tb.shs.n_cols;
+        // (3,Cs) block in float4 chunks; gather the term columns
         const float* sd = m.shs_deform4;
         for (int t = 0; t < tb.shs.n; ++t) {
             const float w = tb.shs.w0[t];
@@ -358,13 +358,9 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
             dfl[1] = g2.w;
             dfl[2] = g3.x;
         }
-        if (visible) {
-            const float3 p = make_float3(sv0.x, sv0.y, sv0.z);
-            float cv[6], dcov[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) cv[i] = a.cov3D[(size_t)g * 6 + i];
-            float3 dm = cov2d_bwd(p, a.rp, cv, cam.view, g0.z, g0.w, g1.x, dcov);
-            const float3 dm2 = mean_proj_depth_bwd(p, cam.view, cam.proj, g0.x, g0.y, g2.y, a.rp.inv_depth);
+        const float3 p = make_float3(sv0.x, sv0.y, sv0.z);
+        float3 dm3 = make_float3(0.f, 0.f, 0.f);
+        auto sh_block = [&]() {
             const float4 sv2 = a.saved[(size_t)g * 3 + 2];
             const float4* sh4 = reinterpret_cast<const float4*>(m.sh4);
             float sh[48];
@@ -383,7 +379,40 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
             sh[1] = sv2.y;
             sh[2] = sv2.z;
             const float dcol[3] = {g1.z, g1.w, g2.x};
-            const float3 dm3 = sh_to_rgb_bwd(deg, p, cam.campos, sh, a.clamped[g], dcol, dsh);
+            dm3 = sh_to_rgb_bwd(deg, p, cam.campos, sh, a.clamped[g], dcol, dsh);
+        };
+        auto sh_store = [&]() {
+            float4* gsh4 = reinterpret_cast<float4*>(a.g.sh4);
+#pragma unroll
+            for (int q = 0; q < 12; ++q)
+                put4(gsh4 + (size_t)q * N + g, make_float4(dsh[4 * q], dsh[4 * q + 1], dsh[4 * q + 2], dsh[4 * q + 3]),
+                     a.accumulate);
+            if (a.g.shs_deform4 && Cs > 0) {
+                const int nq = (3 * Cs + 3) / 4;
+                float4* gsd = reinterpret_cast<float4*>(a.g.shs_deform4);
+                // the DC gradient by channel as scalars: a run-time index into dsh[] would push the whole array
+                // into local memory
+                const float dc0 = dsh[0], dc1 = dsh[1], dc2 = dsh[2];
+                for (int q = 0; q < nq; ++q) {
+                    float v[4];
+#pragma unroll
+                    for (int e4 = 0; e4 < 4; ++e4) {
+                        const int e = 4 * q + e4;
+                        const int c = e / Cs;
+                        const float dc = c == 0 ? dc0 : (c == 1 ? dc1 : dc2);
+                        v[e4] = (c < 3) ? dc * s_wshs[e - c * Cs] : 0.f;
+                    }
+                    put4(gsd + (size_t)q * N + g, make_float4(v[0], v[1], v[2], v[3]), a.accumulate);
+                }
+            }
+        };
+        if (visible) {
+            float cv[6], dcov[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) cv[i] = a.cov3D[(size_t)g * 6 + i];
+            float3 dm = cov2d_bwd(p, a.rp, cv, cam.view, g0.z, g0.w, g1.x, dcov);
+            const float3 dm2 = mean_proj_depth_bwd(p, cam.view, cam.proj, g0.x, g0.y, g2.y, a.rp.inv_depth);
+            sh_block();
             dxt[0] = dm.x + dm2.x + dm3.x;
             dxt[1] = dm.y + dm2.y + dm3.y;
             dxt[2] = dm.z + dm2.z + dm3.z;
@@ -396,25 +425,7 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
             put(a.g.xyz + 3 * (size_t)g + d, dxt[d] + dfl[d], a.accumulate);
             put(a.g.scaling + 3 * (size_t)g + d, dscale[d] * scale[d], a.accumulate);
         }
-        float4* gsh4 = reinterpret_cast<float4*>(a.g.sh4);
-#pragma unroll
-        for (int q = 0; q < 12; ++q)
-            put4(gsh4 + (size_t)q * N + g, make_float4(dsh[4 * q], dsh[4 * q + 1], dsh[4 * q + 2], dsh[4 * q + 3]),
-                 a.accumulate);
-        if (a.g.shs_deform4 && Cs > 0) {
-            const int nq = (3 * Cs + 3) / 4;
-            float4* gsd = reinterpret_cast<float4*>(a.g.shs_deform4);
-            for (int q = 0; q < nq; ++q) {
-                float v[4];
-#pragma unroll
-                for (int e4 = 0; e4 < 4; ++e4) {
-                    const int e = 4 * q + e4;
-                    const int c = e / Cs;
-                    v[e4] = (c < 3) ? dsh[c] * s_wshs[e - c * Cs] : 0.f;
-                }
-                put4(gsd + (size_t)q * N + g, make_float4(v[0], v[1], v[2], v[3]), a.accumulate);
-            }
-        }
+        sh_store();
         // opacity: op_act = sigmoid(o) [* mask]
         {
             const float dop = g1.y;
@@ -1125,6 +1136,8 @@ __global__ void background_finalize_multi_kernel(const __grid_constant__ MultiVi
 
 void launch_fused_forward(const FusedFwdArgs& a, int N, cudaStream_t stream)
 {
+    // sweep r1w: reading the (3,Cs) colour-deformation block as whole float4 chunks with dense weights instead of
+    // the 3 n scalar gathers: 0.145 vs 0.135 ms (slower: the scalar loads hit the same L1 lines) -- dropped
     // measured on B200 (profiles/README.md, sweep r1d): 128 threads x 8 CTAs/SM (64 registers) 0.135 ms,
     // 256 x 3 (80 registers) 0.153 ms -- latency-bound on HBM, so occupancy beats the few spilled words
     static const int v = tune_variant("ADGS_TUNE_FWD", 0);
@@ -1141,6 +1154,9 @@ void launch_fused_backward(const FusedBwdArgs& a, int N, cudaStream_t stream)
     // sweep r1d: 128 x 4 (128 registers) 0.220 ms, 256 x 2 0.229 ms; 96 / 80 registers spill and lose (0.26 / 0.32 ms)
     static const int v = tune_variant("ADGS_TUNE_PGB", 0);
     switch (v) {
+    // sweep r1w: the run-time index dsh[e / Cs] had put the 48-float SH gradient array into local memory; with the DC
+    // gradient in scalars 0.221 -> 0.201 ms. Consuming / storing the SH block before the covariance chain: no
+    // change (0.200); 5 CTAs/SM at 96 registers 0.219-0.227 ms
     case 1: fused_backward_kernel<256, 2><<<(N + 255) / 256, 256, 0, stream>>>(a); break;
     default: fused_backward_kernel<128, 4><<<(N + 127) / 128, 128, 0, stream>>>(a); break;
     }
