@@ -598,6 +598,47 @@ def run_ours(args):
         train_it = {"ms_per_iteration": per_mode, "note": "render + L1/SSIM/depth/obj/sky losses + backward + fused Adam "
                     "(18 groups), one view per iteration like train.py; not part of value/e2e"}
 
+    # ---- densification: densify_and_prune of the whole model incl. Adam moments, and the
+    #      near-index K-NN, each timed on its own with synthetic statistics; runs last: it changes the model --------
+    densify = None
+    if ex is None and mv is None:
+        from adgs_b200 import densify as DN
+        model.scene_extent, model.object_extent, model.percent_dense = 20.0, 5.0, 0.01
+        model.training_setup(targs, window_aware=False)
+        n_all = model.get_pts_num
+        gen = torch.Generator(device=device).manual_seed(7)
+        ms_runs, rows = [], None
+        for rep in range(2):   # the first run grows the caching allocator; the second is the steady-state cost
+            model.denom = torch.randint(0, 4, (model.get_pts_num, 1), generator=gen, device=device).float()
+            model.xyz_gradient_accum = model.denom * 0.0002 * torch.exp(torch.randn((model.get_pts_num, 1), generator=gen,
+                                                                                    device=device))
+            n_before = model.get_pts_num
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            model.densify_and_prune(0.0002, 0.0002, 0.005, False)
+            torch.cuda.synchronize()
+            ms_runs.append((time.perf_counter() - t0) * 1e3)
+            rows = (n_before, model.get_pts_num)
+        per_g = 380 + 1052 * wl["obj_frac"]
+        pts4 = torch.cat([model.xyz.detach()[model.n_scene:], model.gs_time.reshape(-1, 1) * 20.0], dim=-1).contiguous()
+        anchors = pts4[torch.randperm(pts4.shape[0], device=device)[:pts4.shape[0] // 8]].contiguous()
+        DN.knn_points(anchors, pts4, 8)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            DN.knn_points(anchors, pts4, 8)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_knn = e0.elapsed_time(e1) / 3
+        densify = {"densify_and_prune_ms": round(ms_runs[-1], 3), "first_call_ms": round(ms_runs[0], 3),
+                   "rows_before_after": rows,
+                   "algorithmic_bytes": int(3 * per_g * (rows[0] + rows[1])),
+                   "knn_points_ms": round(ms_knn, 3), "knn_anchors_points_K": [anchors.shape[0], pts4.shape[0], 8],
+                   "knn_pairs_per_s": round(anchors.shape[0] * pts4.shape[0] / (ms_knn * 1e-3), 1),
+                   "note": "host wall time incl. allocation of the new arrays and the one read-back of the row counts; "
+                           "parameters + both Adam moments gathered in one launch; not part of value/e2e"}
+        model.optimizer = None
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline()
@@ -620,6 +661,7 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": round(launches, 1), "clocks": clocks,
             "roofline": roof, "step_roofline": step_roof, "stage_ms": {k: round(v, 4) for k, v in (stage_ms or {}).items()},
             "cpu_baseline": cpu_base, "optimizer_step": adam, "loss_front_end": loss_fe, "train_iteration": train_it,
+            "densification": densify,
         }
         print(json.dumps(line))
     if world > 1:
