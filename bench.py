@@ -601,14 +601,24 @@ def run_ours(args):
     # ---- densification: densify_and_prune of the whole model incl. Adam moments, and the
     #      near-index K-NN, each timed on its own with synthetic statistics; runs last: it changes the model --------
     densify = None
-    if ex is None and mv is None:
+
+    def densify_section():
         from adgs_b200 import densify as DN
-        model.scene_extent, model.object_extent, model.percent_dense = 20.0, 5.0, 0.01
-        model.training_setup(targs, window_aware=False)
-        n_all = model.get_pts_num
+        from adgs_b200.gaussian_model import PARAM_NAMES as _PN
         gen = torch.Generator(device=device).manual_seed(7)
         ms_runs, rows = [], None
-        for rep in range(2):   # the first run grows the caching allocator; the second is the steady-state cost
+        model.optimizer = None
+        # every run starts from the same 1 M-Gaussian parameters (a copy of the bench model with fresh Adam state):
+        # the first run grows the caching allocator, the later ones are the steady-state cost inside a training run
+        base = {k: getattr(model, k).detach().clone() for k in _PN}
+        base_time, base_ns, base_no = model.gs_time.clone(), model.n_scene, model.n_obj
+        for rep in range(3):
+            for k in _PN:
+                setattr(model, k, torch.nn.Parameter(base[k].clone()))
+            model.gs_time, model.n_scene, model.n_obj = base_time.clone(), base_ns, base_no
+            model.scene_extent, model.object_extent, model.percent_dense = 20.0, 5.0, 0.01
+            model.training_setup(targs, window_aware=False)
+            model.object_extent = 5.0
             model.denom = torch.randint(0, 4, (model.get_pts_num, 1), generator=gen, device=device).float()
             model.xyz_gradient_accum = model.denom * 0.0002 * torch.exp(torch.randn((model.get_pts_num, 1), generator=gen,
                                                                                     device=device))
@@ -619,6 +629,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             ms_runs.append((time.perf_counter() - t0) * 1e3)
             rows = (n_before, model.get_pts_num)
+        del base
         per_g = 380 + 1052 * wl["obj_frac"]
         pts4 = torch.cat([model.xyz.detach()[model.n_scene:], model.gs_time.reshape(-1, 1) * 20.0], dim=-1).contiguous()
         anchors = pts4[torch.randperm(pts4.shape[0], device=device)[:pts4.shape[0] // 8]].contiguous()
@@ -630,13 +641,19 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         ms_knn = e0.elapsed_time(e1) / 3
-        densify = {"densify_and_prune_ms": round(ms_runs[-1], 3), "first_call_ms": round(ms_runs[0], 3),
+        return {"densify_and_prune_ms": round(min(ms_runs[1:]), 3), "first_call_ms": round(ms_runs[0], 3),
                    "rows_before_after": rows,
                    "algorithmic_bytes": int(3 * per_g * (rows[0] + rows[1])),
                    "knn_points_ms": round(ms_knn, 3), "knn_anchors_points_K": [anchors.shape[0], pts4.shape[0], 8],
                    "knn_pairs_per_s": round(anchors.shape[0] * pts4.shape[0] / (ms_knn * 1e-3), 1),
                    "note": "host wall time incl. allocation of the new arrays and the one read-back of the row counts; "
                            "parameters + both Adam moments gathered in one launch; not part of value/e2e"}
+
+    if ex is None and mv is None:
+        try:
+            densify = densify_section()
+        except Exception as exc:   # an auxiliary measurement must never take the headline line down with it
+            densify = {"error": f"{type(exc).__name__}: {exc}"}
         model.optimizer = None
 
     cpu_base = None
