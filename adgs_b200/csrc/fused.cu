@@ -13,6 +13,7 @@
 //   scale     = exp(s)                                            (:88-91)
 // and runs the per-Gaussian rasterizer front end (forward.cu:155-256) in the same registers, so
 // the deformed tensors never round-trip HBM. 48 bytes per Gaussian are kept for the backward.
+#include <mutex>
 #include "api_internal.cuh"
 #include "trajectory.cuh"
 
@@ -1283,16 +1284,19 @@ struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
     bool ok = false;
+    std::mutex mu;  // the fork .. join enqueue sequence of one backward must not interleave with another host thread's
 };
 
 SideStream& side_stream()
 {
     static SideStream table[64];
     static bool tried[64] = {};
+    static std::mutex init_mu;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     SideStream& s = table[dev];
+    std::lock_guard<std::mutex> lock(init_mu);
     if (!tried[dev]) {
         tried[dev] = true;
         s.ok = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -1475,8 +1479,10 @@ int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const 
     static const int fill_variant = tune_variant("ADGS_TUNE_FILL", 0);
     bool fills_done = false;
     SideStream* side = nullptr;
+    std::unique_lock<std::mutex> side_lock;
     if (fill_variant == 0 && !basis->sparse_grads && model->N_obj > 0 && !cam->debug) {
         side = &side_stream();
+        if (side->ok) side_lock = std::unique_lock<std::mutex>(side->mu);
         if (side->ok && cudaEventRecord(side->fork, stream) == cudaSuccess &&
             cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess) {
             issue_gradient_fills(model, basis, grads, 0, bg_scratch, side->stream);
@@ -1488,6 +1494,7 @@ int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const 
                             bs, is, capacity, img_opacity, dpix, grad_record, gs.counters, stream);
     if (fills_done && cudaStreamWaitEvent(stream, side->join, 0) != cudaSuccess)   // always join, even on error
         return record_cuda_error(cudaGetLastError(), "gradient fill join");
+    if (side_lock.owns_lock()) side_lock.unlock();
     if (st) return st;
     return run_per_gaussian_backward(cam, model, basis, radii, gs.cov3D, gs.clamped, saved4, grad_record, grads, 0,
                                      dL_dmeans2D, dq_scratch, bg_scratch, stream, fills_done);

@@ -57,6 +57,8 @@ def test_struct_sizes_match_header():
     assert C.sizeof(L.QuatBasis) == 16 + 32
     assert C.sizeof(L.TimeBasis) == 4 * 488 + 48 + 16
     assert C.sizeof(L.Model) == 8 + 11 * 8
+    assert C.sizeof(L.DensifyParams) == 14 * 4
+    assert C.sizeof(L.GatherSegment) == 2 * 8 + 8 * 4
 
 
 def test_bad_arguments_are_rejected_without_a_gpu():
