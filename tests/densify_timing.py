@@ -8,7 +8,8 @@
   * knn_points (adgs_knn_points) vs a chunked torch cdist + topk
   * add_densification_stats (one launch) vs the reference's four indexed torch ops
 
-Writes gpurun_out/densify_timing.json. Usage (GPU box): python tools/densify_timing.py
+Lives under tests/ because it reuses the parity tests' model builders (which import oracle/); it is measurement
+infrastructure, not collected by pytest. Writes gpurun_out/densify_timing.json. Usage (GPU box): python tests/densify_timing.py
 """
 import json
 import os
@@ -20,7 +21,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 from adgs_b200 import densify as D  # noqa: E402
 from adgs_b200 import scenes  # noqa: E402
