@@ -73,6 +73,20 @@ class DensifyStats:
         self.max_radii = torch.zeros(n, device=device)
 
     def add_view(self, viewspace_grad: torch.Tensor, visibility_filter: torch.Tensor, radii: torch.Tensor):
+        if self.grad_norm_sum.is_cuda:
+            # one launch (adgs_densify_stats; visibility_filter is radii > 0, gaussian_renderer/__init__.py:104):
+            # 0.015 ms at 1 M Gaussians instead of 2.7 ms for the four indexed torch ops below
+            from . import _lib as L
+            dev = self.grad_norm_sum.device
+            g = viewspace_grad.contiguous()
+            r = radii.to(torch.int32).contiguous()
+            with torch.cuda.device(dev):
+                st = L.load().adgs_densify_stats(r.shape[0], L.ptr(g), L.ptr(r), L.ptr(self.grad_norm_sum),
+                                                 L.ptr(self.visible_count), L.ptr(self.max_radii),
+                                                 torch.cuda.current_stream(dev).cuda_stream)
+            L.check(st, "densify_stats")
+            return
+        # host tensors (the gloo tests of the reduction logic)
         vis = visibility_filter
         self.grad_norm_sum[vis] += torch.norm(viewspace_grad[vis, :2], dim=-1, keepdim=True)
         self.visible_count[vis] += 1

@@ -194,11 +194,17 @@ def test_multi_view_step_sums_view_gradients():
                                  render_objmask=True)
     cot_fn = lambda v, r: ((r["render"], r["depth"], r["img_flow"]), (cot["color"], cot["depth"][0], cot["flow"]))
     want = None
+    n_pts = model.get_pts_num
+    w_norm, w_cnt, w_rad = torch.zeros(n_pts, 1).cuda(), torch.zeros(n_pts, 1).cuda(), torch.zeros(n_pts).cuda()
     for v in views:
         model.zero_grad()
         res = render_fn(v)
         outs, cots = cot_fn(v, res)
         torch.autograd.backward(outs, cots)
+        vis = res["visibility_filter"]                      # the reference's per-view statistics, with torch ops
+        w_norm[vis] += torch.norm(res["viewspace_points"].grad[vis, :2], dim=-1, keepdim=True)
+        w_cnt[vis] += 1
+        w_rad[vis] = torch.max(w_rad[vis], res["radii"][vis].float())
         g = {k: getattr(model, k).grad.clone() for k in ("xyz", "sh4", "xyz_deform", "rot_deform", "gs_time_sigma",
                                                           "background_deform")}
         want = g if want is None else {k: want[k] + g[k] for k in g}
@@ -208,6 +214,8 @@ def test_multi_view_step_sums_view_gradients():
         assert Hh.rel_err(got[k], want[k]) <= 1e-5, k
         assert getattr(model, k).grad.data_ptr() == got[k].data_ptr()
     assert mv.stats.visible_count.max().item() <= 3 and mv.stats.visible_count.sum().item() > 0
+    assert torch.equal(mv.stats.visible_count, w_cnt) and torch.equal(mv.stats.max_radii, w_rad)
+    assert Hh.rel_err(mv.stats.grad_norm_sum, w_norm) <= 1e-5
 
 
 def test_splat_exchange_step_matches_multi_view_step():
