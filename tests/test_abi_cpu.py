@@ -66,3 +66,40 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert lib.adgs_mark_visible(-1, None, None, None, None, None) == -1
     assert lib.adgs_sort_pairs(None, None, None, None, 10, 0, 40, None, None) == -1
     assert lib.adgs_rasterize_backward(None, None, None, None, 0, None, None, None, None, None, None, None) == -1
+
+
+def test_densify_and_knn_reject_bad_arguments_without_a_gpu():
+    """Argument validation of the densification / K-NN entry points returns before any CUDA call."""
+    lib = L.load()
+    p = L.DensifyParams(N_scene=10, N_obj=5, mode=L.DENSIFY_AND_PRUNE, n_split=2)
+    tot = (C.c_int32 * 8)()
+    assert lib.adgs_densify_classify(None, None, None, None, None, None, None, tot, None) == -1
+    assert lib.adgs_densify_classify(C.byref(p), None, None, None, None, None, None, tot, None) == -1   # no workspace
+    ws = (C.c_char * 4096)()
+    base = C.addressof(ws)
+    aligned = (base + 15) & ~15
+    assert lib.adgs_densify_classify(C.byref(p), None, None, None, None, None, aligned, tot, None) == -1   # inputs missing
+    assert lib.adgs_densify_classify(C.byref(p), None, None, None, None, None, aligned + 4, tot, None) == -1  # alignment
+    bad = L.DensifyParams(N_scene=10, N_obj=5, mode=7, n_split=2)
+    assert lib.adgs_densify_classify(C.byref(bad), None, None, None, None, None, aligned, tot, None) == -1
+    pr = L.DensifyParams(N_scene=10, N_obj=5, mode=L.DENSIFY_PRUNE_ONLY, n_split=1)
+    assert lib.adgs_densify_classify(C.byref(pr), None, None, None, None, None, aligned, tot, None) == -1   # no mask
+    assert lib.adgs_densify_workspace_bytes(1000, 500) >= 1500
+    assert lib.adgs_densify_workspace_bytes(10**6, 10**6) > lib.adgs_densify_workspace_bytes(1000, 500)
+    assert lib.adgs_densify_plan(C.byref(p), None, tot, None, None, None) == -1
+    seg = (L.GatherSegment * 1)()
+    assert lib.adgs_densify_gather(seg, L.GATHER_MAX_SEGMENTS + 1, None, None, None) == -1
+    seg[0].planes, seg[0].width, seg[0].dst_rows = 1, 5, 4                       # width must be 1..4
+    assert lib.adgs_densify_gather(seg, 1, None, None, None) == -1
+    seg[0].width, seg[0].dst_rows = 4, 0                                         # nothing to write: no launch
+    assert lib.adgs_densify_gather(seg, 1, None, None, None) == 0
+    assert lib.adgs_densify_stats(-1, None, None, None, None, None, None) == -1
+    assert lib.adgs_densify_stats(0, None, None, None, None, None, None) == 0
+    assert lib.adgs_reset_opacity(0, 0.01, None, None, None, None) == 0
+    assert lib.adgs_reset_opacity(5, 0.01, None, None, None, None) == -1
+    # K-NN: K <= 32, D in {3, 4}, K <= P
+    assert lib.adgs_knn_points(4, 100, 3, 33, None, None, None, None, None, None) == -4
+    assert lib.adgs_knn_points(4, 100, 5, 8, None, None, None, None, None, None) == -4
+    assert lib.adgs_knn_points(4, 6, 3, 8, None, None, None, None, None, None) == -1
+    assert lib.adgs_knn_points(0, 100, 3, 8, None, None, None, None, None, None) == 0
+    assert lib.adgs_knn_points_workspace_bytes(1000, 10**5, 8) >= 1000 * 8 * 8

@@ -45,3 +45,59 @@ def test_adam_step_rejects_bad_arguments_without_a_gpu():
     assert lib.adgs_adam_step(seg, 1, 0.9, 0.999, 1e-15, 1, None) == -1
     seg[0].n = 0                                                              # empty segments are skipped: no launch
     assert lib.adgs_adam_step(seg, 1, 0.9, 0.999, 1e-15, 1, None) == 0
+
+
+def _cpu_model(ns=5, no=3):
+    import torch
+    from adgs_b200.gaussian_model import GaussianModel
+    oa = {"xyz": [6, 3, 0, 2, 0, 0], "rotation": [0, 0, 0, 0, 5, 2], "shs": [0, 0, 0, 2, 0, 0], "background": [6, 3, 0, 2, 0, 0]}
+    g = torch.Generator().manual_seed(0)
+    R = lambda *s: torch.randn(*s, generator=g)
+    ref = dict(scene_xyz=R(ns, 3), obj_xyz=R(no, 3), scene_shs_dc=R(ns, 1, 3), obj_shs_dc=R(no, 1, 3),
+               scene_shs_rest=R(ns, 15, 3), obj_shs_rest=R(no, 15, 3), scene_opacity=R(ns, 1), obj_opacity=R(no, 1),
+               scene_scaling=R(ns, 3), obj_scaling=R(no, 3), scene_rotation=R(ns, 4), obj_rotation=R(no, 4),
+               xyz_deform_param=R(no, 3, 10), rotation_deform_param=R(no, 4, 5), shs_deform_param_scene=R(ns, 3, 4),
+               shs_deform_param_obj=R(no, 3, 4), background_deform_param=R(1, 3, 10), gs_time=torch.rand(no, 1),
+               gs_time_sigma=R(no, 2))
+    return GaussianModel.from_reference(ref, oa, device="cpu")
+
+
+def test_segments_skip_arrays_without_gradient_like_torch_adam():
+    """torch.optim.Adam skips parameters whose .grad is None (the iteration of a densification: every
+    per-Gaussian tensor is new and only deform_background still has its gradient) and counts steps per parameter;
+    FusedAdam builds segments only for arrays that have a gradient and keeps one step count per array."""
+    import torch
+    from adgs_b200.gaussian_model import PARAM_NAMES
+    from adgs_b200.optimizer import FusedAdam
+    m = _cpu_model()
+    opt = FusedAdam(m, {n: 1e-3 for n in GROUP_NAMES})
+    assert opt._segments() == [] and opt.step_count == 0
+    m.background_deform.grad = torch.zeros_like(m.background_deform)
+    segs = opt._segments()
+    assert [k for k, _ in segs] == ["background_deform"] and segs[0][1].n == m.background_deform.numel()
+    for k in PARAM_NAMES:
+        getattr(m, k).grad = torch.zeros_like(getattr(m, k))
+    assert [k for k, _ in opt._segments()] == list(PARAM_NAMES)
+    # the xyz segment carries both learning rates and the scene / object split
+    xyz = dict(opt._segments())["xyz"]
+    assert xyz.lr_rule == L.ADAM_LR_SPLIT and xyz.split == 3 * m.n_scene
+    opt.step_counts["background_deform"] = 7
+    assert opt.step_count == 7
+    opt.step_count = 3
+    assert set(opt.step_counts.values()) == {3}
+
+
+def test_shared_arrays_need_equal_learning_rates():
+    import pytest
+    import torch
+    from adgs_b200.gaussian_model import PARAM_NAMES
+    from adgs_b200.optimizer import FusedAdam
+    m = _cpu_model()
+    opt = FusedAdam(m, {n: 1e-3 for n in GROUP_NAMES})
+    for k in PARAM_NAMES:
+        getattr(m, k).grad = torch.zeros_like(getattr(m, k))
+    for g in opt.param_groups:
+        if g["name"] == "obj_scaling":
+            g["lr"] = 2e-3
+    with pytest.raises(ValueError):
+        opt._segments()
