@@ -9,8 +9,8 @@
 //
 // Design: exact brute force, A x P pairs. With A = P / K anchors there are too few anchors to fill 148 SMs with
 // one thread per anchor, so the cloud is cut into S slices: CTA (x, s) answers 128 anchors against slice s,
-// staging the slice through shared memory (one float4 per point, broadcast reads) and keeping each anchor's
-// K best in registers; a second pass merges the S sorted partial lists of an anchor.
+// staging the slice through shared memory (points in pairs for the packed FP32x2 pipe, broadcast reads) and keeping
+// each anchor's K best in registers; a second pass merges the S sorted partial lists of an anchor.
 #include <cfloat>
 #include "api_internal.cuh"
 
@@ -40,12 +40,17 @@ __device__ __forceinline__ void knn_insert(float (&bd)[K], int (&bi)[K], float d
     }
 }
 
+// Points are staged in PAIRS so that the distance arithmetic runs on the packed FP32x2 pipe (FADD2 / FMUL2 / FFMA2,
+// two points per instruction): pair jp of a tile is {x0, x1, y0, y1}, {z0, z1, w0, w1}. Every component is the same
+// IEEE operation sequence as the scalar form (q - v as one rounding, then one multiply and D - 1 fused
+// multiply-adds), so distances and therefore the returned indices are bit-identical to the scalar kernel.
 template <int D, int K>
 __global__ void __launch_bounds__(kAnchors)
 knn_partial_kernel(int A, int P, const float* __restrict__ anchors, const float* __restrict__ points, int slice_len,
                    float* __restrict__ part_d, int* __restrict__ part_i)
 {
-    __shared__ float4 tile[kTile];
+    __shared__ float4 tile_xy[kTile / 2];
+    __shared__ float4 tile_zw[kTile / 2];
     const int a = blockIdx.x * kAnchors + threadIdx.x;
     const int s = blockIdx.y, S = gridDim.y;
     const int p0 = s * slice_len, p1 = min(P, p0 + slice_len);
@@ -53,6 +58,9 @@ knn_partial_kernel(int A, int P, const float* __restrict__ anchors, const float*
     if (a < A)
 #pragma unroll
         for (int d = 0; d < D; ++d) q[d] = anchors[(size_t)a * D + d];
+    const float2 qx = make_float2(q[0], q[0]), qy = make_float2(q[1], q[1]), qz = make_float2(q[2], q[2]),
+                 qw = make_float2(q[3], q[3]);
+    const float2 neg1 = make_float2(-1.f, -1.f);
     float bd[K];
     int bi[K];
 #pragma unroll
@@ -60,34 +68,46 @@ knn_partial_kernel(int A, int P, const float* __restrict__ anchors, const float*
         bd[j] = FLT_MAX;
         bi[j] = -1;
     }
+    float* sxy = reinterpret_cast<float*>(tile_xy);
+    float* szw = reinterpret_cast<float*>(tile_zw);
     for (int base = p0; base < p1; base += kTile) {
         const int n = min(kTile, p1 - base);
+        const int n_pairs = (n + 1) >> 1;
         __syncthreads();
-        for (int j = threadIdx.x; j < n; j += kAnchors) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float* src = points + (size_t)(base + j) * D;
-            v.x = src[0];
-            v.y = src[1];
-            v.z = src[2];
-            if (D == 4) v.w = src[3];
-            tile[j] = v;
+        for (int j = threadIdx.x; j < 2 * n_pairs; j += kAnchors) {
+            // an odd tail is padded with a point at infinity: its distance is +inf and never beats a candidate
+            float x = __int_as_float(0x7f800000), y = 0.f, z = 0.f, w = 0.f;
+            if (j < n) {
+                const float* src = points + (size_t)(base + j) * D;
+                x = src[0];
+                y = src[1];
+                z = src[2];
+                if (D == 4) w = src[3];
+            }
+            const int o = 4 * (j >> 1) + (j & 1);
+            sxy[o] = x;
+            sxy[o + 2] = y;
+            szw[o] = z;
+            szw[o + 2] = w;
         }
         __syncthreads();
         if (a < A) {
 #pragma unroll 4
-            for (int j = 0; j < n; ++j) {
-                const float4 v = tile[j];
-                float diff = q[0] - v.x;
-                float dist = diff * diff;
-                diff = q[1] - v.y;
-                dist += diff * diff;
-                diff = q[2] - v.z;
-                dist += diff * diff;
+            for (int jp = 0; jp < n_pairs; ++jp) {
+                const float4 vxy = tile_xy[jp];
+                const float4 vzw = tile_zw[jp];
+                float2 diff = __ffma2_rn(make_float2(vxy.x, vxy.y), neg1, qx);  // q - v, one rounding
+                float2 dist = __fmul2_rn(diff, diff);
+                diff = __ffma2_rn(make_float2(vxy.z, vxy.w), neg1, qy);
+                dist = __ffma2_rn(diff, diff, dist);
+                diff = __ffma2_rn(make_float2(vzw.x, vzw.y), neg1, qz);
+                dist = __ffma2_rn(diff, diff, dist);
                 if (D == 4) {
-                    diff = q[3] - v.w;
-                    dist += diff * diff;
+                    diff = __ffma2_rn(make_float2(vzw.z, vzw.w), neg1, qw);
+                    dist = __ffma2_rn(diff, diff, dist);
                 }
-                knn_insert<K>(bd, bi, dist, base + j);
+                knn_insert<K>(bd, bi, dist.x, base + 2 * jp);      // lower index first: ties keep it
+                knn_insert<K>(bd, bi, dist.y, base + 2 * jp + 1);
             }
         }
     }
