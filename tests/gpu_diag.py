@@ -1,6 +1,6 @@
 """GPU diagnostic: libadgs_b200 vs the reference built in oracle/_ref vs the numpy oracle.
 Prints mismatch statistics instead of asserting (the asserting versions live in tests/).
-Usage (on the GPU box): python tools/gpu_diag.py [--big]
+Lives under tests/ (it imports oracle/). Usage (on the GPU box): python tests/gpu_diag.py [--big]
 """
 import argparse
 import os
