@@ -317,6 +317,7 @@ SIGNATURES = {
     "adgs_env_backward": (C.c_int, [_P(EnvMap), C.c_int32, C.c_int32, C.c_float] + [C.c_void_p] * 6),
     "adgs_env_adam_step": (C.c_int, [_P(EnvMap), C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]),
     "adgs_launch_count": (C.c_ulonglong, []),
+    "adgs_selftest_exp_pair": (C.c_int, [C.c_void_p, C.c_void_p]),
     "adgs_profile_begin": (C.c_int, []),
     "adgs_profile_num_stages": (C.c_int, []),
     "adgs_profile_stage_name": (C.c_char_p, [C.c_int]),

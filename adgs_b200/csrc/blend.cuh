@@ -79,6 +79,22 @@ __device__ __forceinline__ bool splat_may_touch_rect(float mx, float my, float A
     return !(best < thresh - eps);  // NaN compares false -> keep
 }
 
+// Level-1 cull: does the splat's bounding box (packed half extents, pack_splat_extent) reach the rectangle of
+// pixel centres with centre (cx, cy) and half size (wx, wy)? NaN extents never hit, +inf always.
+__device__ __forceinline__ bool splat_bbox_hits_rect(float mx, float my, float packed_extent, float cx, float cy,
+                                                     float wx, float wy)
+{
+    const uint32_t bits = __float_as_uint(packed_extent);
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&bits));
+    return fabsf(mx - cx) <= h.x + wx && fabsf(my - cy) <= h.y + wy;
+}
+
+// cull threshold of the exact test from the opacity: -log(255 op), 1e30 if op <= 0
+__device__ __forceinline__ float splat_cull_threshold(float op)
+{
+    return op > 0.f ? -__logf(255.f * op) : 1e30f;
+}
+
 void launch_blend_forward(const BlendFwdArgs& a, bool has_flow, cudaStream_t stream);
 void launch_blend_backward(const BlendBwdArgs& a, bool has_flow, cudaStream_t stream);
 

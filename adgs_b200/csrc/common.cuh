@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstddef>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include "../../include/adgs_b200.h"
 
 #define ADGS_BLOCK_X 16
@@ -17,9 +18,12 @@
 #define ADGS_REC_FLOATS 16 /* packed per-Gaussian blend record, 64 B */
 #define ADGS_GRAD_FLOATS 16 /* packed per-Gaussian blend gradient record, 64 B */
 
-// Record layout (floats): 0 x, 1 y, 2 conic.x, 3 conic.y, 4 conic.z, 5 opacity, 6..8 rgb,
-// 9 depth feature (depth or 1/(depth+1e-7)), 10..12 flow point, 13 semantic[0], 14 depth,
-// 15 cull threshold -log(255*opacity) (1e30 if opacity <= 0)
+// Record layout (floats), one 16-byte quad per consumer so that every field group is a single LDS.128:
+//   q0 = 0 x, 1 y, 2 conic.x, 3 conic.y          (cull test + alpha evaluation)
+//   q1 = 4 conic.z, 5 opacity, 6 depth, 7 half2 {hx, hy}: conservative half extents (pixels) of the region
+//        where the splat can reach alpha >= 1/255 (NaN = nowhere, +inf = unknown / keep everywhere)
+//   q2 = 8..10 rgb, 11 depth feature (depth or 1/(depth+1e-7))
+//   q3 = 12..14 flow point, 15 semantic[0]
 // Gradient record layout: 0,1 dmean2D  2,3,4 dconic(x,y,w)  5 dopacity  6..8 dcolor
 // 9 ddepthfeat  10..12 dflow  13 dsemantic[0]
 
@@ -131,6 +135,38 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p)
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v)
 {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Conservative axis-aligned half extents of {d : alpha(d) >= 1/255} for a splat with conic (A, B, C) and
+// opacity op: alpha >= 1/255 <=> -0.5 d'Qd >= -log(255 op) =: -t, an ellipse whose bounding box is
+// hx = sqrt(2 t C / det), hy = sqrt(2 t A / det). Slack: t is raised by 0.02 and by the rounding error of the
+// per-pixel evaluation (which grows with the anisotropy A C / det), det is lowered by its own rounding error,
+// and the result is rounded UP to half precision. Packed as the bits of a half2 in a float slot.
+__device__ __forceinline__ float pack_splat_extent(float A, float B, float C, float op)
+{
+    const uint32_t kNever = 0x7FFF7FFFu, kAlways = 0x7C007C00u;  // half NaN / +inf in both lanes
+    if (!(op > 0.f)) return __uint_as_float(kNever);
+    const float t0 = __logf(255.f * op) + 0.02f;
+    if (!(t0 > 0.f)) return __uint_as_float(t0 != t0 ? kAlways : kNever);
+    const float AC = A * C, BB = B * B;
+    const float det = (AC - BB) - 4e-7f * (AC + BB);
+    if (!(A > 0.f && C > 0.f && det > 0.f)) return __uint_as_float(kAlways);
+    const float inv = 1.0f / det;
+    const float t = 2.0f * t0 * (1.0f + 1e-5f * AC * inv);
+    const float hx = sqrtf(t * C * inv) * 1.0001f + 0.01f, hy = sqrtf(t * A * inv) * 1.0001f + 0.01f;
+    const __half2 h = __halves2half2(__float2half_ru(hx), __float2half_ru(hy));
+    return __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+}
+
+// The 64-byte blend record of one splat (layout above).
+__device__ __forceinline__ void store_blend_record(float4* rec, float px, float py, float conic_x, float conic_y,
+                                                   float conic_z, float opacity, float depth, const float* rgb,
+                                                   float depth_feature, float fx, float fy, float fz, float sem0)
+{
+    rec[0] = make_float4(px, py, conic_x, conic_y);
+    rec[1] = make_float4(conic_z, opacity, depth, pack_splat_extent(conic_x, conic_y, conic_z, opacity));
+    rec[2] = make_float4(rgb[0], rgb[1], rgb[2], depth_feature);
+    rec[3] = make_float4(fx, fy, fz, sem0);
 }
 
 // fire-and-forget float add (RED.E.ADD.F32)

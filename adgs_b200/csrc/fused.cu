@@ -252,11 +252,8 @@ __global__ void __launch_bounds__(TPB, MINB) fused_forward_kernel(const __grid_c
     c2[2] = make_float2(sg.cov3D[4], sg.cov3D[5]);
     const float dfeat = a.rp.inv_depth ? (1.0f / (sg.depth + 0.0000001f)) : sg.depth;
     const float sem0 = (a.render_objmask && is_obj) ? 1.f : 0.f;
-    float4* rec = a.record + (size_t)g * 4;
-    rec[0] = make_float4(sg.px, sg.py, sg.conic_x, sg.conic_y);
-    rec[1] = make_float4(sg.conic_z, op, rgb[0], rgb[1]);
-    rec[2] = make_float4(rgb[2], dfeat, flow ? xf[0] : 0.f, flow ? xf[1] : 0.f);
-    rec[3] = make_float4(flow ? xf[2] : 0.f, sem0, sg.depth, op > 0.f ? -__logf(255.f * op) : 1e30f);
+    store_blend_record(a.record + (size_t)g * 4, sg.px, sg.py, sg.conic_x, sg.conic_y, sg.conic_z, op, sg.depth, rgb, dfeat,
+                       flow ? xf[0] : 0.f, flow ? xf[1] : 0.f, flow ? xf[2] : 0.f, sem0);
     a.radii[g] = sg.radius;
     a.tiles_touched[g] = sg.tiles;
     a.depth_keys[g] = __float_as_uint(sg.depth);
@@ -760,11 +757,8 @@ __global__ void __launch_bounds__(TPB, MINB) shard_forward_multi_kernel(const __
         c2[2] = make_float2(sg.cov3D[4], sg.cov3D[5]);
         const float dfeat = V.rp.inv_depth ? (1.0f / (sg.depth + 0.0000001f)) : sg.depth;
         const float sem0 = (a.render_objmask && is_obj) ? 1.f : 0.f;
-        float4* rec = V.record + (size_t)g * 4;
-        rec[0] = make_float4(sg.px, sg.py, sg.conic_x, sg.conic_y);
-        rec[1] = make_float4(sg.conic_z, op, rgb[0], rgb[1]);
-        rec[2] = make_float4(rgb[2], dfeat, flow ? xf[0] : 0.f, flow ? xf[1] : 0.f);
-        rec[3] = make_float4(flow ? xf[2] : 0.f, sem0, sg.depth, op > 0.f ? -__logf(255.f * op) : 1e30f);
+        store_blend_record(V.record + (size_t)g * 4, sg.px, sg.py, sg.conic_x, sg.conic_y, sg.conic_z, op, sg.depth, rgb,
+                           dfeat, flow ? xf[0] : 0.f, flow ? xf[1] : 0.f, flow ? xf[2] : 0.f, sem0);
         V.radii[g] = sg.radius;
         V.tiles_touched[g] = sg.tiles;
         V.depth_keys[g] = __float_as_uint(sg.depth);

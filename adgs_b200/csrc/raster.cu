@@ -98,12 +98,8 @@ __global__ void __launch_bounds__(256) preprocess_aos_kernel(const PreprocessArg
     const float sem0 = (a.D_S == 1 && a.semantic) ? a.semantic[idx] : 0.f;
     const float dfeat = a.rp.inv_depth ? (1.0f / (g.depth + 0.0000001f)) : g.depth;
 
-    float4* rec = a.record + (size_t)idx * 4;
-    rec[0] = make_float4(g.px, g.py, g.conic_x, g.conic_y);
-    rec[1] = make_float4(g.conic_z, a.opacities[idx], rgb[0], rgb[1]);
-    rec[2] = make_float4(rgb[2], dfeat, fl[0], fl[1]);
-    const float op = a.opacities[idx];
-    rec[3] = make_float4(fl[2], sem0, g.depth, op > 0.f ? -__logf(255.f * op) : 1e30f);
+    store_blend_record(a.record + (size_t)idx * 4, g.px, g.py, g.conic_x, g.conic_y, g.conic_z, a.opacities[idx], g.depth,
+                       rgb, dfeat, fl[0], fl[1], fl[2], sem0);
 
     a.radii[idx] = g.radius;
     a.tiles_touched[idx] = g.tiles;

@@ -527,6 +527,11 @@ ADGS_API int adgs_env_adam_step(const adgs_env_map* env, double lr, double beta1
  * per stage, the summed milliseconds and the number of timed scopes.
  * ---------------------------------------------------------------------------------------- */
 ADGS_API unsigned long long adgs_launch_count(void);
+
+/* Device self-test of the blend kernels' packed (FP32x2) exponential against CUDA's expf() -- the function the
+ * reference's renderCUDA calls (RZ/cuda_rasterizer/forward.cu:345, backward.cu:560) -- over every float bit pattern
+ * of its domain [-87, 87] plus NaN. out (device, 2 x uint64): [0] mismatching bit patterns, [1] patterns checked. */
+ADGS_API int adgs_selftest_exp_pair(unsigned long long* out, adgs_stream_t stream);
 ADGS_API int adgs_profile_begin(void);
 ADGS_API int adgs_profile_num_stages(void);
 ADGS_API const char* adgs_profile_stage_name(int stage);

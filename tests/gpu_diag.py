@@ -42,13 +42,13 @@ def compare_case(name, c, check_oracle=False, backward=True):
     both = vis & (radii_o > 0)
     if both.any():
         print("means2D max abs diff:", (rec[both, 0:2] - ir["means2D"][both]).abs().max().item())
-        print("depth bit mismatches:", (rec[both, 14].view(torch.int32) != ir["depths"][both].view(torch.int32)).sum().item())
+        print("depth bit mismatches:", (rec[both, 6].view(torch.int32) != ir["depths"][both].view(torch.int32)).sum().item())
         con_o = torch.stack([rec[both, 2], rec[both, 3], rec[both, 4], rec[both, 5]], 1)
         print("conic_opacity bit mismatches:", (con_o.view(torch.int32) != ir["conic_opacity"][both].view(torch.int32)).sum().item(),
               " rel err:", Hh.rel_err(con_o, ir["conic_opacity"][both]))
         if c["sh"].numel():
-            print("rgb rel err:", Hh.rel_err(rec[both, 6:9], ir["rgb"][both]),
-                  " rgb bit mismatches:", (rec[both, 6:9].contiguous().view(torch.int32) != ir["rgb"][both].contiguous().view(torch.int32)).sum().item())
+            print("rgb rel err:", Hh.rel_err(rec[both, 8:11], ir["rgb"][both]),
+                  " rgb bit mismatches:", (rec[both, 8:11].contiguous().view(torch.int32) != ir["rgb"][both].contiguous().view(torch.int32)).sum().item())
             cl_o = io["clamped"][both]
             cl_r = ir["clamped"][both]
             cl_r_bits = (cl_r[:, 0].int() | (cl_r[:, 1].int() << 1) | (cl_r[:, 2].int() << 2))
@@ -56,7 +56,7 @@ def compare_case(name, c, check_oracle=False, backward=True):
         if ir.get("cov3D") is not None and c["scales"].numel():
             print("cov3D bit mismatches:", (io["cov3D"][both].contiguous().view(torch.int32) != ir["cov3D"][both].contiguous().view(torch.int32)).sum().item())
     if R_o == R_r and R_o > 0:
-        keys_o = (io["point_list_tile"].long() << 32) | (rec[io["point_list"].long(), 14].view(torch.int32).long() & 0xFFFFFFFF)
+        keys_o = (io["point_list_tile"].long() << 32) | (rec[io["point_list"].long(), 6].view(torch.int32).long() & 0xFFFFFFFF)
         print("sorted key mismatches:", (keys_o != ir["point_list_keys"]).sum().item(), "of", R_o)
         print("point_list mismatches:", (io["point_list"] != ir["point_list"]).sum().item())
     print("ranges mismatches:", (io["ranges"] != ir["ranges"]).sum().item())

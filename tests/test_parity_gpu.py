@@ -67,10 +67,10 @@ def test_forward_backward_vs_reference(name):
     assert torch.equal(io["tiles_touched"], ir["tiles_touched"]), "tiles_touched"
     vis = ref[4] > 0
     rec = io["record"]
-    assert torch.equal(rec[vis, 14].view(torch.int32), ir["depths"][vis].view(torch.int32)), "depth bits"
+    assert torch.equal(rec[vis, 6].view(torch.int32), ir["depths"][vis].view(torch.int32)), "depth bits"
     assert torch.equal(rec[vis, 0:2], ir["means2D"][vis]), "means2D"
     if R:
-        keys = (io["point_list_tile"].long() << 32) | (rec[io["point_list"].long(), 14].view(torch.int32).long()
+        keys = (io["point_list_tile"].long() << 32) | (rec[io["point_list"].long(), 6].view(torch.int32).long()
                                                         & 0xFFFFFFFF)
         assert torch.equal(keys, ir["point_list_keys"]), "sorted keys"
         assert torch.equal(io["point_list"], ir["point_list"]), "point_list"
@@ -245,7 +245,7 @@ def test_full_size_properties():
     io = Hh.inspect_ours(out[5], out[6], out[7], P, R, W, H)
     assert int(io["tiles_touched"].long().sum()) == R
     tiles = io["point_list_tile"].long()
-    depth = io["record"][io["point_list"].long(), 14]
+    depth = io["record"][io["point_list"].long(), 6]
     key = (tiles << 32) | (depth.view(torch.int32).long() & 0xFFFFFFFF)
     assert (key[1:] >= key[:-1]).all(), "instances sorted by (tile, depth)"
     same = key[1:] == key[:-1]
