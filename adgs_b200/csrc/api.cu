@@ -128,6 +128,7 @@ int bin_and_blend(const adgs_camera* cam, int P, int D_S, bool has_flow, const f
     b.out_semantic = out->semantic;
     b.counters = gs.counters;
     b.capacity = (uint32_t)capacity;
+    b.cull_mask = bs.cull_mask;
     {
         StageScope sc(kStageBlendFwd, stream);
         launch_blend_forward(b, has_flow, stream);
@@ -420,6 +421,7 @@ int adgs_rasterize_backward(const adgs_camera* cam, const adgs_gaussians* g, con
     b.grad_record = grad_record;
     b.dL_dsemantic_g = grads->dL_dsemantic;
     b.counters = nullptr;  // exact binning: the arena was sized from num_rendered
+    b.cull_mask = bs.cull_mask;
     if (D_S > 1 && !grads->dL_dsemantic) return ADGS_ERR_ARG;
     if (R > 0) {
         {

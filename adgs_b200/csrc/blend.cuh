@@ -19,6 +19,7 @@ struct BlendFwdArgs {
     float* out_semantic;
     const uint32_t* counters;    // [0]=num_rendered [1]=overflow (range clamp in async mode)
     uint32_t capacity;
+    uint8_t* cull_mask;          // [R] out: which of the tile's eight 8x4 sub-tiles each instance can reach
 };
 
 struct BlendBwdArgs {
@@ -37,6 +38,7 @@ struct BlendBwdArgs {
     const float* dL_dopacity;
     float* grad_record;    // [P][16] zero-initialised accumulation target
     float* dL_dsemantic_g; // (P,D_S) for D_S > 1 (zero-initialised)
+    const uint8_t* cull_mask;  // [R] the forward's per-instance sub-tile masks: the backward culls by table look-up
     const uint32_t* counters;  // [1] = binning overflow of the forward (sync-free mode): leave the
                                // gradient record zero instead of reading images that were never written
 };

@@ -261,6 +261,7 @@ struct BinningState {
     uint32_t* keys_b;
     uint32_t* vals_a;  // [R] gaussian id per instance
     uint32_t* vals_b;
+    uint8_t* cull_mask;  // [R] per sorted instance: bit s = sub-tile s of its tile passed the forward's exact cull
     SortWorkspace sort;
     static BinningState from_chunk(char*& chunk, size_t R)
     {
@@ -270,6 +271,7 @@ struct BinningState {
         carve(chunk, b.keys_b, R);
         carve(chunk, b.vals_a, R);
         carve(chunk, b.vals_b, R);
+        carve(chunk, b.cull_mask, R + 256);
         b.sort = SortWorkspace::from_chunk(chunk, R);
         return b;
     }

@@ -1224,6 +1224,7 @@ int run_blend_backward(const adgs_camera* cam, int P, int render_objmask, bool h
     b.grad_record = grad_record;
     b.dL_dsemantic_g = nullptr;
     b.counters = counters;
+    b.cull_mask = bs.cull_mask;
     if (capacity > 0) {
         StageScope sc(kStageBlendBwd, stream);
         launch_blend_backward(b, has_flow, stream);
