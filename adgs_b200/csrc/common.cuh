@@ -51,6 +51,15 @@ struct Mat3 {
     float c[3][3];
 };
 
+// a0 b0 + a1 b1 + a2 b2 with the FMA contraction PINNED to what nvcc emits for the reference's expression
+// (left product fused, middle product rounded on its own): fma(a2, b2, fma(a0, b0, a1 * b1)). Explicit intrinsics,
+// because the compiler's choice of which product to fuse depends on the code around the expression, and the strict
+// and the fused front ends must agree bit for bit with each other and with the reference kernels.
+__device__ __forceinline__ float dot3_pinned(float a0, float b0, float a1, float b1, float a2, float b2)
+{
+    return __fmaf_rn(a2, b2, __fmaf_rn(a0, b0, __fmul_rn(a1, b1)));
+}
+
 __device__ __forceinline__ Mat3 mat3_mul(const Mat3& a, const Mat3& b)
 {
     Mat3 r;
@@ -58,7 +67,7 @@ __device__ __forceinline__ Mat3 mat3_mul(const Mat3& a, const Mat3& b)
     for (int col = 0; col < 3; ++col) {
 #pragma unroll
         for (int row = 0; row < 3; ++row) {
-            r.c[col][row] = a.c[0][row] * b.c[col][0] + a.c[1][row] * b.c[col][1] + a.c[2][row] * b.c[col][2];
+            r.c[col][row] = dot3_pinned(a.c[0][row], b.c[col][0], a.c[1][row], b.c[col][1], a.c[2][row], b.c[col][2]);
         }
     }
     return r;

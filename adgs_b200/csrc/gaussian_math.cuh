@@ -33,40 +33,47 @@ struct SplatGeom {
     float cov3D[6];
 };
 
-// y = M[:, :3] x + M[:, 3] for the transposed-in-memory 4x4 (m[col*4+row]).
+// y = M[:, :3] x + M[:, 3] for the transposed-in-memory 4x4 (m[col*4+row]); contraction pinned (dot3_pinned).
 __device__ __forceinline__ float3 xform_point_4x3(const float3& p, const float* m)
 {
     float3 r;
-    r.x = m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12];
-    r.y = m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13];
-    r.z = m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14];
+    r.x = __fadd_rn(dot3_pinned(m[0], p.x, m[4], p.y, m[8], p.z), m[12]);
+    r.y = __fadd_rn(dot3_pinned(m[1], p.x, m[5], p.y, m[9], p.z), m[13]);
+    r.z = __fadd_rn(dot3_pinned(m[2], p.x, m[6], p.y, m[10], p.z), m[14]);
     return r;
 }
 
 __device__ __forceinline__ float4 xform_point_4x4(const float3& p, const float* m)
 {
     float4 r;
-    r.x = m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12];
-    r.y = m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13];
-    r.z = m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14];
-    r.w = m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15];
+    r.x = __fadd_rn(dot3_pinned(m[0], p.x, m[4], p.y, m[8], p.z), m[12]);
+    r.y = __fadd_rn(dot3_pinned(m[1], p.x, m[5], p.y, m[9], p.z), m[13]);
+    r.z = __fadd_rn(dot3_pinned(m[2], p.x, m[6], p.y, m[10], p.z), m[14]);
+    r.w = __fadd_rn(dot3_pinned(m[3], p.x, m[7], p.y, m[11], p.z), m[15]);
     return r;
 }
 
 // Rotation matrix of the UN-normalised quaternion (w,x,y,z) in column-major storage, with the
-// element placement of the reference's constructor call (forward.cu:134-138).
+// element placement of the reference's constructor call (forward.cu:134-138). Every product of two
+// quaternion components feeds two entries (x y in 2(xy - rz) and 2(xy + rz), ...); which of the two products of
+// an entry nvcc rounds on its own and which it fuses is pinned here to what it emits for the reference's
+// expression in preprocessCUDA (read off the SASS; tests/test_parity_gpu.py holds cov3D / conic bit-exact).
 __device__ __forceinline__ Mat3 quat_to_mat3(float r, float x, float y, float z)
 {
+    const float zx = __fmul_rn(z, x), xr = __fmul_rn(x, r), zr = __fmul_rn(z, r);
+    const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+    auto twice = [](float v) { return __fadd_rn(v, v); };
+    auto one_minus = [](float v) { return __fadd_rn(-v, 1.f); };
     Mat3 R;
-    R.c[0][0] = 1.f - 2.f * (y * y + z * z);
-    R.c[0][1] = 2.f * (x * y - r * z);
-    R.c[0][2] = 2.f * (x * z + r * y);
-    R.c[1][0] = 2.f * (x * y + r * z);
-    R.c[1][1] = 1.f - 2.f * (x * x + z * z);
-    R.c[1][2] = 2.f * (y * z - r * x);
-    R.c[2][0] = 2.f * (x * z - r * y);
-    R.c[2][1] = 2.f * (y * z + r * x);
-    R.c[2][2] = 1.f - 2.f * (x * x + y * y);
+    R.c[0][0] = one_minus(twice(__fadd_rn(yy, zz)));
+    R.c[0][1] = twice(__fmaf_rn(y, x, -zr));
+    R.c[0][2] = twice(__fmaf_rn(y, r, zx));
+    R.c[1][0] = twice(__fmaf_rn(y, x, zr));
+    R.c[1][1] = one_minus(twice(__fmaf_rn(x, x, zz)));
+    R.c[1][2] = twice(__fmaf_rn(z, y, -xr));
+    R.c[2][0] = twice(__fmaf_rn(y, -r, zx));
+    R.c[2][1] = twice(__fmaf_rn(z, y, xr));
+    R.c[2][2] = one_minus(twice(__fmaf_rn(x, x, yy)));
     return R;
 }
 
@@ -185,7 +192,7 @@ __device__ __forceinline__ bool splat_geometry(const float3& p, const float* sca
     cov2d_project(p, rp, g.cov3D, view, ctx);
     const float cx = ctx.a, cy = ctx.b, cz = ctx.c;
 
-    const float det = (cx * cz - cy * cy);
+    const float det = __fmaf_rn(cx, cz, -__fmul_rn(cy, cy));  // cx cz - cy cy, contraction pinned
     if (det == 0.0f) return false;
     const float det_inv = 1.f / det;
     g.conic_x = cz * det_inv;
@@ -193,8 +200,9 @@ __device__ __forceinline__ bool splat_geometry(const float3& p, const float* sca
     g.conic_z = cx * det_inv;
 
     const float mid = 0.5f * (cx + cz);
-    const float lambda1 = mid + sqrtf(max(0.1f, mid * mid - det));
-    const float lambda2 = mid - sqrtf(max(0.1f, mid * mid - det));
+    const float disc = sqrtf(max(0.1f, __fmaf_rn(mid, mid, -det)));
+    const float lambda1 = mid + disc;
+    const float lambda2 = mid - disc;
     const float my_radius = ceilf(3.f * sqrtf(max(lambda1, lambda2)));
     g.px = ndc_to_pix(p_proj.x, rp.W);
     g.py = ndc_to_pix(p_proj.y, rp.H);

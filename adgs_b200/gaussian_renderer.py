@@ -52,7 +52,9 @@ class _FusedRender(torch.autograd.Function):
         deformed = {"opacity": opacity_act}
         if materialize:
             deformed.update(xyz=torch.empty((N, 3), **o), rotation=torch.empty((N, 4), **o),
-                            shs=torch.empty((N, 16, 3), **o))
+                            shs=torch.empty((N, 16, 3), **o), scaling=torch.empty((N, 3), **o))
+            if flow_t is not None:
+                deformed["flow_xyz"] = torch.empty((N, 3), **o)
         tensors = dict(zip(PARAM_NAMES, (xyz, scaling, rotation, opacity, sh4, shs_deform4, xyz_deform, rot_deform,
                                          background_deform, gs_time_sigma)))
         tensors = {k: v.contiguous() for k, v in tensors.items()}
@@ -64,7 +66,8 @@ class _FusedRender(torch.autograd.Function):
             images = L.Images(color=L.ptr(color), depth=L.ptr(depth), opacity=L.ptr(img_opacity), flow=L.ptr(img_flow),
                               semantic=L.ptr(img_sem), radii=L.ptr(radii))
             dfm = L.Deformed(xyz=L.ptr(deformed.get("xyz")), rotation=L.ptr(deformed.get("rotation")),
-                             shs=L.ptr(deformed.get("shs")), opacity=L.ptr(opacity_act), scaling=None, flow_xyz=None)
+                             shs=L.ptr(deformed.get("shs")), opacity=L.ptr(opacity_act),
+                             scaling=L.ptr(deformed.get("scaling")), flow_xyz=L.ptr(deformed.get("flow_xyz")))
             geom = torch.empty((lib.adgs_geometry_bytes(N),), dtype=torch.uint8, device=dev)
             img = torch.empty((lib.adgs_image_bytes(W, H),), dtype=torch.uint8, device=dev)
             saved = torch.empty((lib.adgs_render_saved_bytes(N),), dtype=torch.uint8, device=dev)
@@ -99,7 +102,8 @@ class _FusedRender(torch.autograd.Function):
         ctx.save_for_backward(*[tensors[k] for k in PARAM_NAMES], radii, geom, binning, img, saved, img_opacity)
         ctx.mark_non_differentiable(radii)
         ctx.deformed = deformed
-        extra = tuple(deformed[k] for k in ("xyz", "rotation", "shs")) if materialize else ()
+        extra = tuple(deformed[k] for k in ("xyz", "rotation", "shs", "scaling", "flow_xyz") if k in deformed) \
+            if materialize else ()
         for e in extra:
             ctx.mark_non_differentiable(e)
         ctx.mark_non_differentiable(opacity_act)
@@ -196,7 +200,11 @@ def render(viewpoint_camera, pc: GaussianModel, env_map, pipe, scaling_modifier=
         foreground, radii, depth, img_opacity, img_flow, img_semantic, opacity = out[:7]
         deform_pkg = {'opacity': opacity}
         if materialize:
-            deform_pkg.update(xyz=out[7], rotation=out[8], shs=out[9])
+            # pipe.materialize_deformed: the tensors the reference's get_deformed_pkg / get_deformed_xyz(flow_time) /
+            # get_scaling would have produced, exactly as the fused kernel used them (tests/test_fused_gpu.py)
+            deform_pkg.update(xyz=out[7], rotation=out[8], shs=out[9], scaling=out[10])
+            if flow_time is not None:
+                deform_pkg["flow_xyz"] = out[11]
 
     if env_map is not None and hasattr(env_map, "composite"):
         # adgs_b200.env.EnvironmentMap: background + blend in one kernel (gaussian_renderer/__init__.py:92-94)

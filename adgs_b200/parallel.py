@@ -155,6 +155,80 @@ class MultiViewStep:
         return v
 
 
+class _RawCudaArray:
+    """Zero-copy torch view of raw device memory (torch.as_tensor reads __cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerBuffers:
+    """This rank's exchange buffers, mapped into every rank of the box (adgs_peer_alloc / adgs_peer_open: CUDA IPC
+    over NVLink / NVSwitch), and the flag barrier over them. One allocation per rank:
+
+        flags  (8) u32        barrier flags, one word per peer
+        rec    (G, n, 16) f32 slot r = rank r's 64-byte blend records of THIS rank's view
+        meta   (5, G, n) i32  plane-major (depth key, tiles touched, radius, mean x, mean y), rank-major inside a
+                              plane: exactly the concatenated arrays adgs_splats_bin reads, no permute
+        grec   (G, n, 16) f32 gradient records of this rank's view, written by its own blend backward
+    """
+
+    def __init__(self, L, lib, group, world, rank, n, device):
+        import ctypes as C
+        self.L, self.lib, self.world, self.rank, self.n, self.device = L, lib, world, rank, n, device
+        P = world * n
+        self.off_rec = 512
+        self.off_meta = self.off_rec + P * 64
+        self.off_grec = self.off_meta + 5 * P * 4
+        self.bytes = self.off_grec + P * 64
+        with torch.cuda.device(device):
+            ptr = C.c_void_p()
+            handle = C.create_string_buffer(64)
+            L.check(lib.adgs_peer_alloc(self.bytes, C.byref(ptr), handle), "peer_alloc")
+            self.local = int(ptr.value)
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.base = []
+            for p in range(world):
+                if p == rank:
+                    self.base.append(self.local)
+                else:
+                    q = C.c_void_p()
+                    L.check(lib.adgs_peer_open(handles[p], C.byref(q)), "peer_open")
+                    self.base.append(int(q.value))
+        self.flag_arr = (C.c_void_p * world)(*self.base)        # the flag words sit at offset 0
+        self.status_ptr = self.local + 256
+        self.epoch = 0
+
+    def rec(self, p, slot=0):
+        return self.base[p] + self.off_rec + slot * self.n * 64
+
+    def meta(self, p, plane, slot=0):
+        return self.base[p] + self.off_meta + ((plane * self.world + slot) * self.n) * 4
+
+    def grec(self, p, slot=0):
+        return self.base[p] + self.off_grec + slot * self.n * 64
+
+    def barrier(self, stream):
+        self.epoch += 1
+        self.L.check(self.lib.adgs_peer_barrier(self.world, self.rank, self.flag_arr, self.epoch, self.status_ptr,
+                                                stream), "peer_barrier")
+
+    def local_radii(self):
+        return torch.as_tensor(_RawCudaArray(self.meta(self.rank, 2), (self.world * self.n,), "<i4"), device=self.device)
+
+    def timed_out(self):
+        return bool(torch.as_tensor(_RawCudaArray(self.status_ptr, (1,), "<u4"), device=self.device).item())
+
+    def close(self):
+        for p, b in enumerate(self.base):
+            if p != self.rank:
+                self.lib.adgs_peer_close(b)
+        self.lib.adgs_peer_free(self.local)
+        self.base = []
+
+
 # =====================================================================================================
 # Splat exchange: Gaussians sharded across ranks, every view blended on one rank.
 # =====================================================================================================
@@ -178,7 +252,11 @@ class SplatExchangeStep:
     `cotangent_fn(view, images) -> dict(color, depth, opacity, flow, semantic)` (None = zero).
     """
 
-    def __init__(self, shard, group=None, render_objmask=True):
+    def __init__(self, shard, group=None, render_objmask=True, exchange=None):
+        """exchange: "peer" (default when world > 1) = splats and gradient records travel through peer memory:
+        the front end stores straight into the blending rank's buffers over NVLink, the per-Gaussian backward loads
+        its gradient records from the blending ranks, two flag barriers per step and no collective on the data
+        path; "nccl" = two all_to_all_single per step (also what views_per_rank > 1 uses)."""
         from . import _lib as L
         self.L = L
         self.lib = L.load()
@@ -192,6 +270,10 @@ class SplatExchangeStep:
         self.names = PARAM_NAMES
         self.grads = {k: torch.zeros_like(getattr(shard, k)) for k in PARAM_NAMES}
         self._capacity = 0
+        self.exchange = exchange or os.environ.get("ADGS_EXCHANGE", "peer")
+        assert self.exchange in ("peer", "nccl")
+        self._peer = None
+        self._checks = []   # deferred {num_rendered, overflow} read-backs of sync-free steps
 
     # -- helpers -------------------------------------------------------------------------------------
     def _camera(self, cam, pipe, keep):
@@ -237,6 +319,9 @@ class SplatExchangeStep:
                 ev.record(torch.cuda.current_stream(dev))
                 timing["marks"].append((name, ev))
 
+        self._resolve_checks()
+        if G > 1 and k == 1 and self.exchange == "peer":
+            return self._run_peer(views, cotangent_fn, pipe)
         mark("start")
         o = dict(dtype=torch.float32, device=dev)
         D_S = 1 if self.render_objmask else 0
@@ -349,11 +434,9 @@ class SplatExchangeStep:
                                       dL_dflow=L.ptr(ct["flow"]), dL_dsemantic=L.ptr(ct["semantic"]),
                                       dL_dopacity=L.ptr(ct["opacity"]))
                     if ev is not None:
-                        ev.synchronize()
-                        self._capacity = max(self._capacity, int(1.3 * int(counters[0])) + 65536)
-                        if bool(counters[1]) or int(counters[0]) > capacity:
-                            raise RuntimeError("adgs_b200: binning arena overflow in a sync-free splat-exchange "
-                                               "step; re-run the step (the arena has been enlarged)")
+                        # no host block inside the step: the blend kernels skip an overflowed frame on the device
+                        # (its gradient records stay zero); the counters are looked at before the next step
+                        self._checks.append((counters, ev, capacity))
                     grec = gback[:, 0].view(P, 16) if k == 1 else torch.empty((P, 16), **o)
                     L.check(lib.adgs_splats_backward(C.byref(cc), C.byref(splats), D_S, has_flow, L.ptr(binning),
                                                      int(capacity), L.ptr(imgbuf), L.ptr(img["opacity"]), C.byref(ig),
@@ -392,6 +475,136 @@ class SplatExchangeStep:
                     timing["sums"][n1] = timing["sums"].get(n1, 0.0) + e0.elapsed_time(e1)
                 timing["count"] += 1
             timing["marks"] = []
+        return results, stats
+
+    def _resolve_checks(self):
+        """Counters of earlier sync-free steps: grow the arena; an overflowed step was dropped on the device."""
+        rest = self._checks
+        self._checks = []
+        for counters, ev, capacity in rest:
+            ev.synchronize()
+            R, ovf = int(counters[0]), bool(counters[1])
+            self._capacity = max(self._capacity, int(1.3 * R) + 65536)
+            if ovf or R > capacity:
+                import warnings
+                warnings.warn("adgs_b200: the binning arena overflowed in a sync-free splat-exchange step; that "
+                              "view's images are invalid and its gradient records were left zero on the device; the "
+                              "arena has been enlarged")
+
+    def _bin_view(self, cc, splats, P, W, H, pipe, dev, stream):
+        """Depth sort, scan, instance emission, tile sort, ranges of one view; exact (host reads num_rendered) the
+        first time, sync-free (arena from the running bound, counters read back asynchronously) afterwards."""
+        import ctypes as C
+        L, lib, m = self.L, self.lib, self.model
+        geom = torch.empty((lib.adgs_geometry_bytes(P),), dtype=torch.uint8, device=dev)
+        imgbuf = torch.empty((lib.adgs_image_bytes(W, H),), dtype=torch.uint8, device=dev)
+        if bool(getattr(pipe, "sync_free", True)) and self._capacity > 0:
+            capacity = self._capacity
+            binning = torch.empty((lib.adgs_binning_bytes(capacity),), dtype=torch.uint8, device=dev)
+            L.check(lib.adgs_splats_bin(C.byref(cc), C.byref(splats), L.ptr(geom), L.ptr(binning), capacity,
+                                        L.ALLOC_FN(), None, L.ptr(imgbuf), stream), "splats_bin")
+            counters = m._pinned_counters()
+            L.check(lib.adgs_read_counters(L.ptr(geom), P, counters.data_ptr(), stream), "read_counters")
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self._checks.append((counters, ev, capacity))
+        else:
+            holder = {}
+
+            def _alloc(nbytes, _u, holder=holder):
+                holder["b"] = torch.empty((int(nbytes),), dtype=torch.uint8, device=dev)
+                return holder["b"].data_ptr()
+
+            cb = L.ALLOC_FN(_alloc)
+            R = L.check(lib.adgs_splats_bin(C.byref(cc), C.byref(splats), L.ptr(geom), None, 0, cb, None,
+                                            L.ptr(imgbuf), stream), "splats_bin")
+            binning, capacity = holder["b"], int(R)
+            self._capacity = max(self._capacity, int(1.3 * R) + 65536)
+        return geom, imgbuf, binning, int(capacity)
+
+    def _run_peer(self, views, cotangent_fn, pipe):
+        """run() for one view per rank with the exchange through peer memory (PeerBuffers): per round
+        front end of my shard for all G views, stores landing in the blending ranks -> barrier -> bin + blend my
+        view forward and backward from / into my own buffers -> barrier -> per-Gaussian backward of my shard, the
+        gradient records of view v loaded from rank v."""
+        import ctypes as C
+        L, lib, m = self.L, self.lib, self.model
+        G, r, n, dev = self.world, self.rank, m.get_pts_num, m.xyz.device
+        assert len(views) % G == 0 and G <= 8
+        if self._peer is None or self._peer.n != n:
+            if self._peer is not None:
+                self._peer.close()
+            self._peer = PeerBuffers(L, lib, self.group, G, r, n, dev)
+        pb = self._peer
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        results, stats = [], []
+        first = True
+        o = dict(dtype=torch.float32, device=dev)
+        D_S = 1 if self.render_objmask else 0
+        P = G * n
+        for rnd in range(len(views) // G):
+            batch = views[rnd * G:(rnd + 1) * G]
+            keep = []
+            with torch.cuda.device(dev):
+                state = torch.empty((G, lib.adgs_shard_state_bytes(n)), dtype=torch.uint8, device=dev)
+                cams = [self._camera(cam, pipe, keep) for cam, _ in batch]
+                bases = [m.time_basis(cam.time, flow_t) for cam, flow_t in batch]
+                cam_arr = (L.Camera * G)(*cams)
+                basis_arr = (L.TimeBasis * G)(*bases)
+                # view v's outputs of MY Gaussians go to slot r of rank v's buffers
+                splat_arr = (L.Splats * G)(*[L.Splats(P=n, _pad=0, record=pb.rec(v, r), depth_keys=pb.meta(v, 0, r),
+                                                      tiles_touched=pb.meta(v, 1, r), radii=pb.meta(v, 2, r),
+                                                      mean_x=pb.meta(v, 3, r), mean_y=pb.meta(v, 4, r))
+                                             for v in range(G)])
+                state_arr = (C.c_void_p * G)(*[state[v].data_ptr() for v in range(G)])
+                cmodel = m.c_model()
+                L.check(lib.adgs_shard_forward_multi(G, cam_arr, C.byref(cmodel), basis_arr, int(self.render_objmask),
+                                                     splat_arr, state_arr, stream), "shard_forward_multi")
+                pb.barrier(stream)          # every rank's splats of my view have landed
+                cam, flow_t = batch[r]
+                cc = cams[r]
+                H, W = int(cam.image_height), int(cam.image_width)
+                splats = L.Splats(P=P, _pad=0, record=pb.rec(r), depth_keys=pb.meta(r, 0), tiles_touched=pb.meta(r, 1),
+                                  radii=pb.meta(r, 2), mean_x=pb.meta(r, 3), mean_y=pb.meta(r, 4))
+                geom, imgbuf, binning, capacity = self._bin_view(cc, splats, P, W, H, pipe, dev, stream)
+                img = dict(color=torch.empty((3, H, W), **o), depth=torch.empty((1, H, W), **o),
+                           opacity=torch.empty((1, H, W), **o), flow=torch.empty((3, H, W), **o),
+                           semantic=torch.empty((D_S, H, W), **o))
+                images = L.Images(color=L.ptr(img["color"]), depth=L.ptr(img["depth"]), opacity=L.ptr(img["opacity"]),
+                                  flow=L.ptr(img["flow"]), semantic=L.ptr(img["semantic"]), radii=None)
+                has_flow = int(flow_t is not None)
+                L.check(lib.adgs_splats_blend(C.byref(cc), C.byref(splats), D_S, has_flow, C.byref(images), L.ptr(geom),
+                                              L.ptr(binning), capacity, L.ptr(imgbuf), stream), "splats_blend")
+                res = {"render": img["color"], "depth": img["depth"][0], "img_opacity": img["opacity"][0],
+                       "img_flow": img["flow"] if has_flow else None,
+                       "img_semantic": img["semantic"] if self.render_objmask else None, "radii": pb.local_radii()}
+                results.append(res)
+                cot = cotangent_fn((cam, flow_t), res)
+                ct = {kk: (None if cot.get(kk) is None else cot[kk].contiguous()) for kk in
+                      ("color", "depth", "opacity", "flow", "semantic")}
+                ig = L.ImageGrads(dL_dcolor=L.ptr(ct["color"]), dL_ddepth=L.ptr(ct["depth"]), dL_dflow=L.ptr(ct["flow"]),
+                                  dL_dsemantic=L.ptr(ct["semantic"]), dL_dopacity=L.ptr(ct["opacity"]))
+                L.check(lib.adgs_splats_backward(C.byref(cc), C.byref(splats), D_S, has_flow, L.ptr(binning), capacity,
+                                                 L.ptr(imgbuf), L.ptr(img["opacity"]), C.byref(ig), pb.grec(r), stream),
+                        "splats_backward")
+                pb.barrier(stream)          # every rank's gradient records are complete
+                scratch = torch.empty((lib.adgs_shard_scratch_bytes(G, m.n_obj),), dtype=torch.uint8, device=dev)
+                gm = m.c_model_from(self.grads, with_time=False)
+                d2 = torch.empty((G, n, 3), **o)
+                radii_arr = (C.c_void_p * G)(*[pb.meta(v, 2, r) for v in range(G)])     # peer loads
+                grec_arr = (C.c_void_p * G)(*[pb.grec(v, r) for v in range(G)])         # peer loads
+                d2_arr = (C.c_void_p * G)(*[d2[v].data_ptr() for v in range(G)])
+                L.check(lib.adgs_shard_backward_multi(G, cam_arr, C.byref(cmodel), basis_arr, radii_arr, state_arr,
+                                                      grec_arr, C.byref(gm), int(not first), d2_arr, L.ptr(scratch),
+                                                      stream), "shard_backward_multi")
+                first = False
+                for v in range(G):
+                    # radii of my Gaussians in view v: a view of rank v's buffer (valid until the next step)
+                    stats.append((d2[v], torch.as_tensor(_RawCudaArray(pb.meta(v, 2, r), (n,), "<i4"), device=dev)))
+        if self.grads["background_deform"].numel():
+            dist.all_reduce(self.grads["background_deform"], op=dist.ReduceOp.SUM, group=self.group)
+        for name in self.names:
+            getattr(m, name).grad = self.grads[name]
         return results, stats
 
     def timing_report(self):

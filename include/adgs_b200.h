@@ -397,6 +397,27 @@ ADGS_API int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cam
                               char* scratch, adgs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Peer memory for the splat exchange (one process per GPU, all GPUs of one NVSwitch box). The reference has no
+ * distributed code (train.py:55-61 renders one view per iteration on one GPU), so there is no counterpart.
+ *   adgs_peer_alloc    device buffer (zero-filled) that other processes of the box can map + its 64-byte handle
+ *   adgs_peer_open     map a peer's buffer from its handle -> a device pointer valid in THIS process; kernels of
+ *                      this library may store to / load from it like local memory (the traffic is NVLink)
+ *   adgs_peer_barrier  stream-ordered barrier between the `world` ranks: flag_arrays[p] = rank p's flag array
+ *                      (ADGS_MAX_PEERS words inside a peer buffer, zero at start) as mapped in this process;
+ *                      `epoch` must grow by one per barrier and be the same on every rank. When the barrier
+ *                      completes on a rank's stream, everything every rank queued before ITS barrier has completed
+ *                      (peer stores included). status (local device word): set to 1 if a peer did not arrive in ~2 s.
+ * ---------------------------------------------------------------------------------------- */
+#define ADGS_MAX_PEERS 8
+#define ADGS_PEER_HANDLE_BYTES 64
+ADGS_API int adgs_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+ADGS_API int adgs_peer_open(const unsigned char* handle64, void** ptr);
+ADGS_API int adgs_peer_close(void* ptr);
+ADGS_API int adgs_peer_free(void* ptr);
+ADGS_API int adgs_peer_barrier(int32_t world, int32_t rank, uint32_t* const* flag_arrays, uint32_t epoch,
+                               uint32_t* status, adgs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Optimizer step: replaces `gaussians.optimizer.step()` of train.py:163-167
  * for the torch.optim.Adam(l, lr=0.0, eps=1e-15) that GaussianModel.training_setup builds over 18
  * parameter groups (scene/gaussian_model.py:346-372). One launch updates every array of adgs_model;

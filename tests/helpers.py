@@ -123,6 +123,19 @@ def rel_err(a, b):
     return (a - b).abs().max().item() / denom
 
 
+def elementwise_err(a, b, rtol=1e-4, atol_frac=1e-6):
+    """Element-wise companion of rel_err: an element FAILS if |a-b| > rtol*|b| + atol with
+    atol = atol_frac * max|b| (so that entries down to a millionth of the largest one are held to the relative
+    bound instead of hiding behind the max norm). Returns (failing fraction, worst |a-b| / (rtol*|b| + atol))."""
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    if a.numel() == 0:
+        return 0.0, 0.0
+    atol = atol_frac * max(b.abs().max().item(), 1e-30)
+    bound = rtol * b.abs() + atol
+    excess = (a - b).abs() / bound
+    return (excess > 1.0).double().mean().item(), excess.max().item()
+
+
 def to_np(t):
     return None if (t is None or t.numel() == 0) else t.detach().cpu().numpy()
 
