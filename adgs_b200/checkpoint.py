@@ -129,7 +129,7 @@ def load_ply(model: GaussianModel, path, device="cuda"):
     rots = np.stack([f32(el[n]) for n in by_index("rot_")], axis=1)
     (xyz_deform, rot_deform, shs_deform_scene, shs_deform_obj, bg_deform, gs_time, gs_time_sigma, use_time_mask,
      order_args, scene_extent) = torch.load(os.path.join(os.path.dirname(os.path.abspath(path)), "deform.pth"),
-                                            map_location="cpu", weights_only=False)
+                                            map_location="cpu", weights_only=True)   # tensors, Parameters, bool, dict, list, float only
     n_obj = int(obj_mask.sum())
     assert xyz_deform.shape[0] == n_obj
     assert xyz_deform.shape[-1] == get_param_num(order_args["xyz"])

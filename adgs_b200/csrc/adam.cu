@@ -71,18 +71,38 @@ __global__ void __launch_bounds__(kAdamThreads) fused_adam_kernel(const __grid_c
     for (int it = 0; it < kAdamVec; ++it) {
         const long long i = base + ((long long)it * kAdamThreads + threadIdx.x) * 4;
         if (i >= s.n) break;
+        // which of the four elements have a gradient: a plane the backward did not write holds arbitrary bytes and
+        // counts as zero. With plane % 4 != 0 a float4 straddles two planes: decided per element, and the vector
+        // load happens if ANY of them is live (the dead lanes are dropped by selection, never by arithmetic).
+        bool hg[4] = {true, true, true, true};
         bool has_grad = true;
         if (s.plane > 0) {
-            // a float4 never straddles two planes when plane % 4 == 0; otherwise fall back to reading
-            const long long c0 = i / s.plane, c1 = (i + 3) / s.plane;
-            if (c0 == c1 && c0 < 128) has_grad = (s.active[c0 >> 6] >> (c0 & 63)) & 1ull;
+            auto live = [&](long long c) -> bool { return c >= 128 || ((s.active[c >> 6] >> (c & 63)) & 1ull); };
+            const long long c0 = i / s.plane, c3 = (i + 3) / s.plane;
+            if (c0 == c3) {
+                has_grad = live(c0);
+                hg[0] = hg[1] = hg[2] = hg[3] = has_grad;
+            } else {
+                has_grad = false;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    hg[e] = live((i + e) / s.plane);
+                    has_grad |= hg[e];
+                }
+            }
         }
         if (aligned && i + 4 <= s.n) {
             float4 p = *reinterpret_cast<const float4*>(s.param + i);
             float4 m = *reinterpret_cast<const float4*>(s.exp_avg + i);
             float4 v = *reinterpret_cast<const float4*>(s.exp_avg_sq + i);
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_grad) g = __ldcs(reinterpret_cast<const float4*>(s.grad + i));  // read once: streaming
+            if (has_grad) {
+                g = __ldcs(reinterpret_cast<const float4*>(s.grad + i));  // read once: streaming
+                g.x = hg[0] ? g.x : 0.f;
+                g.y = hg[1] ? g.y : 0.f;
+                g.z = hg[2] ? g.z : 0.f;
+                g.w = hg[3] ? g.w : 0.f;
+            }
             adam_update(p.x, g.x, m.x, v.x, seg_step(a, si, i), a);
             adam_update(p.y, g.y, m.y, v.y, seg_step(a, si, i + 1), a);
             adam_update(p.z, g.z, m.z, v.z, seg_step(a, si, i + 2), a);

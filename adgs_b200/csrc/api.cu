@@ -57,6 +57,9 @@ int bin_and_blend(const adgs_camera* cam, int P, int D_S, bool has_flow, const f
     int st;
 
     const bool do_bin = (stages & 1) != 0, do_blend = (stages & 2) != 0;
+    // The onesweep look-back words carry a 30-bit count and the offset scan is 32-bit (sort.cu): the reference's
+    // 64-bit-key sort works up to 2^32 instances, this path to 2^30 - 1 Gaussians / instances. Refuse, never wrap.
+    if (P >= kMaxSortItems || capacity >= kMaxSortItems) return ADGS_ERR_UNSUPPORTED;
     // (1) Gaussians by (depth bits, id): 4 onesweep passes over 8 B/Gaussian.
     if (do_bin) {
         StageScope sc(kStageDepthSort, stream);
@@ -79,6 +82,7 @@ int bin_and_blend(const adgs_camera* cam, int P, int D_S, bool has_flow, const f
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) return record_cuda_error(e, "num_rendered readback");
         capacity = (int64_t)R;
+        if (capacity >= kMaxSortItems) return ADGS_ERR_UNSUPPORTED;
         if (num_rendered) *num_rendered = (int)R;
         binning = binning_alloc(adgs_binning_bytes(capacity), alloc_user);
         if (!binning) return ADGS_ERR_ALLOC;
@@ -353,6 +357,7 @@ int adgs_rasterize_forward_async(const adgs_camera* cam, const adgs_gaussians* g
                                  adgs_stream_t stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (capacity >= kMaxSortItems) return ADGS_ERR_UNSUPPORTED;
     int st = validate(cam, g, out);
     if (st) return st;
     if (g->P == 0) {
@@ -478,6 +483,7 @@ int adgs_sort_pairs(uint32_t* keys_in, uint32_t* vals_in, uint32_t* keys_out, ui
                     int32_t begin_bit, int32_t end_bit, char* workspace, adgs_stream_t stream)
 {
     if (n < 0 || begin_bit < 0 || end_bit > 32 || end_bit <= begin_bit) return ADGS_ERR_ARG;
+    if (n >= kMaxSortItems) return ADGS_ERR_UNSUPPORTED;
     if (n == 0) return 1;
     if (!keys_in || !vals_in || !keys_out || !vals_out || !workspace) return ADGS_ERR_ARG;
     char* c = workspace;

@@ -204,6 +204,7 @@ constexpr int kSortThreads = 256;
 constexpr int kSortItems = 8;
 constexpr int kSortTile = kSortThreads * kSortItems;  // 2048 pairs per CTA step
 constexpr int kMaxPasses = 4;
+constexpr long long kMaxSortItems = 1ll << 30;  // {flag, count} look-back words hold a 30-bit count
 
 struct SortWorkspace {
     uint32_t* hist;     // [kMaxPasses][256] digit histograms

@@ -233,6 +233,9 @@ def reset_opacity(model, cap=0.01):
         st = L.load().adgs_reset_opacity(model.get_pts_num, cap, L.ptr(model.opacity.data), L.ptr(m), L.ptr(v),
                                          _stream(dev))
     L.check(st, "reset_opacity")
+    # the reference installs a NEW Parameter (replace_tensor_to_optimizer, scene/gaussian_model.py:447-461): it has
+    # no gradient, so an optimizer.step() later in the same iteration skips the freshly reset opacities
+    model.opacity.grad = None
 
 
 @torch.no_grad()

@@ -180,7 +180,7 @@ class GaussianModel(nn.Module):
         self.active_sh_degree = 0
         self.max_sh_degree = sh_degree
         self.order_args = order_args
-        self.use_time_mask = True
+        self.use_time_mask = None    # resolved by training_setup (lambda_sigma > 0) unless set, like gaussian_model.py:78,394
         self.n_scene = 0
         self.n_obj = 0
         self._binning_capacity = 0   # running bound on num_rendered for the sync-free path
@@ -216,7 +216,7 @@ class GaussianModel(nn.Module):
 
     @classmethod
     def create_from_pcd(cls, pcd, scene_extent, cameras_extent, frame_gap, default_order_downsample_ratio,
-                        sh_degree=3, order_args=None, use_time_mask=True, device="cuda"):
+                        sh_degree=3, order_args=None, use_time_mask=None, device="cuda"):
         """GaussianModel.create_from_pcd (scene/gaussian_model.py:255-333): initial Gaussians from a point cloud
         with `.points (P,3)`, `.colors (P,3)` in [0,1], `.time (P,1)`, `.obj_id (P,1)` (utils/graphics_utils.py:17-22).
         Scales from the mean squared distance to the 3 nearest neighbours (distCUDA2 -> adgs_dist_cuda2), identity
@@ -369,7 +369,7 @@ class GaussianModel(nn.Module):
         """True while a window-aware optimizer owns the gradients: render backward then leaves inactive
         control-point planes unwritten (one backward per optimizer step only)."""
         opt = self.__dict__.get("optimizer")
-        return bool(opt is not None and getattr(opt, "window_aware", False))
+        return bool(opt is not None and getattr(opt, "window_aware", False) and opt.window_eligible())
 
     def shard(self, rank: int, world: int):
         """Rank `rank`'s slice of the model for the splat-exchange multi-GPU path: contiguous blocks of

@@ -48,6 +48,9 @@ def get_expon_lr_func(lr_init, lr_final, lr_delay_steps=0, lr_delay_mult=1.0, ma
     return helper
 
 
+MAX_WINDOW_COLUMNS = 128   # bits of adgs_adam_segment.active
+
+
 class FusedAdam:
     """Adam over a planar GaussianModel with the reference's 18 parameter groups.
 
@@ -108,6 +111,15 @@ class FusedAdam:
                              f"(the reference gives them the same value, scene/gaussian_model.py:346-370)")
         return self._lr(a)
 
+    def window_eligible(self):
+        """Can the step take 'zero without reading' for inactive control-point planes? The column mask of
+        adgs_adam_segment has MAX_WINDOW_COLUMNS bits; any plane size works (the kernel decides per element where a
+        float4 straddles two planes). The ONE place this is decided: GaussianModel.sparse_deform_grads asks here, so
+        the render backward zero-fills exactly when the step is going to read everything."""
+        m = self.model
+        return bool(self.window_aware and m.xyz_deform.shape[0] <= MAX_WINDOW_COLUMNS and
+                    m.rot_deform.shape[0] <= MAX_WINDOW_COLUMNS)
+
     @property
     def step_count(self):
         return max(self.step_counts.values())
@@ -120,7 +132,7 @@ class FusedAdam:
         """[(array name, adgs_adam_segment)] of the arrays that have a gradient."""
         m = self.model
         n, ns, no = m.n_scene + m.n_obj, m.n_scene, m.n_obj
-        need_active = self.window_aware and (m.xyz_deform.grad is not None or m.rot_deform.grad is not None)
+        need_active = self.window_eligible() and (m.xyz_deform.grad is not None or m.rot_deform.grad is not None)
         active = m.active_columns() if need_active else None
         segs = []
 
@@ -136,7 +148,10 @@ class FusedAdam:
             s = L.AdamSegment(param=p.data_ptr(), grad=p.grad.data_ptr(), exp_avg=st["exp_avg"].data_ptr(),
                               exp_avg_sq=st["exp_avg_sq"].data_ptr(), n=p.numel(), split=split, plane=0,
                               lr_a=lr_a, lr_b=lr_b, lr_rule=rule)
-            if cols is not None and plane > 0 and plane % 4 == 0 and p.numel() // plane <= 128:
+            if cols is not None and plane > 0:
+                # eligibility was decided by window_eligible() when the backward ran (sparse_deform_grads): here the
+                # planes outside `cols` are UNWRITTEN memory, so there is no dense fallback to take
+                assert p.numel() // plane <= MAX_WINDOW_COLUMNS
                 s.plane = plane
                 bits = [0, 0]
                 for c in cols:
@@ -176,7 +191,7 @@ class FusedAdam:
                                         torch.cuda.current_stream(dev).cuda_stream)
             L.check(st, "adam_step")
         if self.window_aware:
-            self.model.reset_active_columns()
+            self.model.reset_active_columns()   # (also counts the backwards of the step when not eligible)
 
     def zero_grad(self, set_to_none=True):
         for k in PARAM_NAMES:
@@ -235,6 +250,9 @@ def training_setup(model, training_args, window_aware=False):
     from .densify import set_obj_near_idx, setup_statistics
     setup_statistics(model)
     lam = lambda k: float(getattr(a, k, 0.0) or 0.0)
+    if model.use_time_mask is None:     # scene/gaussian_model.py:394
+        model.use_time_mask = lam("lambda_sigma") > 0.0
+        model.__dict__.pop("_basis_cache", None)
     model.use_near_idx = lam("lambda_reg") > 0.0 or (lam("lambda_sigma") > 0.0 and lam("lambda_sigma_reg") > 0.0)
     model.near_num = int(getattr(a, "near_num", 0) or 0)
     if model.use_near_idx and model.xyz.is_cuda:

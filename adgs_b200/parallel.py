@@ -113,10 +113,23 @@ class MultiViewStep:
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         from .gaussian_model import PARAM_NAMES
         self.names = PARAM_NAMES
-        self.bucket = FlatGradBucket({k: getattr(model, k) for k in PARAM_NAMES})
-        self.stats = DensifyStats(model.get_pts_num, model.xyz.device)
+        self._sized_for = None
+        self._resize()
+
+    def _resize(self):
+        """(Re)build the flat bucket for the model's current arrays (densification changes their sizes)."""
+        shapes = tuple(tuple(getattr(self.model, k).shape) for k in self.names)
+        if shapes != self._sized_for:
+            self.bucket = FlatGradBucket({k: getattr(self.model, k) for k in self.names})
+            self._sized_for = shapes
 
     def run(self, views, render_fn, cotangent_fn, reduce_stats=True):
+        """Returns the flat bucket's gradient views. `self.stats` afterwards holds THIS run's densification
+        statistics summed / maxed over all ranks' views (fresh buffers every run: all-reducing a buffer that already
+        holds earlier, already-global sums would count them world_size times); the caller folds them into its
+        running accumulators (model.xyz_gradient_accum / denom / max_radii2D, scene/gaussian_model.py:863-867)."""
+        self._resize()
+        self.stats = DensifyStats(self.model.get_pts_num, self.model.xyz.device)
         local = shard_views(views, self.rank, self.world)
         params = {k: getattr(self.model, k) for k in self.names}
         first = True
@@ -577,7 +590,8 @@ class SplatExchangeStep:
                                               L.ptr(binning), capacity, L.ptr(imgbuf), stream), "splats_blend")
                 res = {"render": img["color"], "depth": img["depth"][0], "img_opacity": img["opacity"][0],
                        "img_flow": img["flow"] if has_flow else None,
-                       "img_semantic": img["semantic"] if self.render_objmask else None, "radii": pb.local_radii()}
+                       "img_semantic": img["semantic"] if self.render_objmask else None,
+                       "radii": pb.local_radii()}      # a view of the exchange buffer: valid until the next round
                 results.append(res)
                 cot = cotangent_fn((cam, flow_t), res)
                 ct = {kk: (None if cot.get(kk) is None else cot[kk].contiguous()) for kk in
@@ -599,8 +613,8 @@ class SplatExchangeStep:
                                                       stream), "shard_backward_multi")
                 first = False
                 for v in range(G):
-                    # radii of my Gaussians in view v: a view of rank v's buffer (valid until the next step)
-                    stats.append((d2[v], torch.as_tensor(_RawCudaArray(pb.meta(v, 2, r), (n,), "<i4"), device=dev)))
+                    # radii of my Gaussians in view v: copied out of rank v's buffer (the next round overwrites it)
+                    stats.append((d2[v], torch.as_tensor(_RawCudaArray(pb.meta(v, 2, r), (n,), "<i4"), device=dev).clone()))
         if self.grads["background_deform"].numel():
             dist.all_reduce(self.grads["background_deform"], op=dist.ReduceOp.SUM, group=self.group)
         for name in self.names:

@@ -34,7 +34,11 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # BASELINE.json configs[1]: KITTI-MOT-shaped frame, 1M Gaussians (25 % objects, 32 control points)
     "kitti-375x1242-1M": dict(W=1242, H=375, n=1_000_000, obj_frac=0.25, median_radius_px=3.0),
-    # BASELINE.json configs[2]: one camera of the Waymo-shaped rig, 3M Gaussians (parity / robustness runs, not the bench line)
+    # BASELINE.json configs[2]: Waymo-shaped 3-camera rig (front-left / front / front-right, yaw -45 / 0 / +45 degrees,
+    # scene/dataset_readers.py:261-357), 3M Gaussians filling the three frusta; one step = all three views
+    "waymo-3cam-1066x1600-3M": dict(W=1600, H=1066, n=3_000_000, obj_frac=0.25, median_radius_px=3.0,
+                                    rig_yaw=(-45.0, 0.0, 45.0)),
+    # one camera of that rig
     "waymo-1066x1600-3M": dict(W=1600, H=1066, n=3_000_000, obj_frac=0.25, median_radius_px=3.0),
     # BASELINE.json configs[4]: stress -- 10M Gaussians, median radius 12 px, half of them inside 5 % of the screen
     "stress-1920x1280-10M": dict(W=1920, H=1280, n=10_000_000, obj_frac=0.25, median_radius_px=12.0, cluster=(0.5, 0.05)),
@@ -179,19 +183,57 @@ def algorithmic_bytes(n_scene, n_obj, R, px):
     return total, stages
 
 
+def scene_tensors(wl, device, seed=0):
+    """The seeded synthetic scene of a workload in the REFERENCE's tensor layout (both arms build exactly this)."""
+    import numpy as np
+    from adgs_b200 import scenes
+    n, n_obj = wl["n"], int(wl["n"] * wl["obj_frac"])
+    n_scene = n - n_obj
+    if "rig_yaw" in wl:
+        # a third of the Gaussians in each camera's frustum, shuffled so that scene / object rows mix all three
+        parts, k = [], len(wl["rig_yaw"])
+        for i, yaw in enumerate(wl["rig_yaw"]):
+            cam_i = scenes.make_camera(wl["W"], wl["H"], 90.0, yaw_deg=yaw, time=T_CAMERA)
+            cnt = n // k + (1 if i < n % k else 0)
+            parts.append(scenes.random_cloud(cnt, cam_i, seed=seed + 17 * i, median_radius_px=wl["median_radius_px"]))
+        perm = np.random.default_rng(seed).permutation(n)
+        cloud = {key: np.concatenate([p[key] for p in parts])[perm] for key in parts[0]}
+    else:
+        cam0 = scenes.make_camera(wl["W"], wl["H"], 90.0, time=T_CAMERA)
+        cloud = scenes.random_cloud(n, cam0, seed=seed, median_radius_px=wl["median_radius_px"], cluster=wl.get("cluster"))
+    tensors = scenes.random_model_tensors(n_scene, n_obj, scenes.BENCH_ORDER_ARGS, cloud, seed=seed + 1, device=device)
+    return tensors, n_scene, n_obj
+
+
 def build_ours(wl, device, seed=0):
     import torch
     from adgs_b200 import scenes
     from adgs_b200.gaussian_model import GaussianModel
-    n, n_obj = wl["n"], int(wl["n"] * wl["obj_frac"])
-    n_scene = n - n_obj
-    cam0 = scenes.make_camera(wl["W"], wl["H"], 90.0, time=T_CAMERA)
-    cloud = scenes.random_cloud(n, cam0, seed=seed, median_radius_px=wl["median_radius_px"], cluster=wl.get("cluster"))
-    tensors = scenes.random_model_tensors(n_scene, n_obj, scenes.BENCH_ORDER_ARGS, cloud, seed=seed + 1, device=device)
+    tensors, n_scene, n_obj = scene_tensors(wl, device, seed)
     model = GaussianModel.from_reference(tensors, scenes.BENCH_ORDER_ARGS, device=device)
     del tensors
     torch.cuda.empty_cache()
     return model, n_scene, n_obj
+
+
+def views_of_step(wl, rank, device):
+    """The (camera, t, flow_t) list one rank renders per step: its view of the multi-timestep batch, or -- for a
+    camera rig -- every camera of the rig at this rank's timestep."""
+    from adgs_b200 import scenes
+    if "rig_yaw" in wl:
+        t = T_CAMERA + 0.05 * rank
+        return [(scenes.make_camera(wl["W"], wl["H"], 90.0, yaw_deg=yaw, time=t, device=device), t, t + (T_FLOW - T_CAMERA))
+                for yaw in wl["rig_yaw"]]
+    return [view_for_rank(wl, rank, device)]
+
+
+def make_config(workload, wl, world, views_per_rank):
+    """Identical in both arms (the driver compares it); arm-specific notes travel outside `config`."""
+    return {"workload": workload, "views_per_step": world * views_per_rank, "image": [wl["H"], wl["W"]],
+            "gaussians": wl["n"], "object_fraction": wl["obj_frac"], "control_points": 32, "bspline_order": 5,
+            "fourier_terms": 6, "sh_degree": 3, "flow": True, "objmask": True, "inv_depth": True,
+            "l2": "inputs (>1.5 GB of parameters per step) exceed the 126 MB L2",
+            "parallelism": f"dp{world}: {views_per_rank} view(s) per rank and step, weak scaling"}
 
 
 def view_for_rank(wl, rank, device):
@@ -243,26 +285,28 @@ def run_ours(args):
         return ((res["render"], res["depth"], res["img_opacity"], res["img_flow"], res["img_semantic"]),
                 (c["color"], c["depth"][0], c["opacity"][0], c["flow"], c["semantic"]))
 
-    exchange = world > 1 and args.parallel == "exchange"
+    rig = "rig_yaw" in wl
+    vpr = len(wl["rig_yaw"]) if rig else 1          # views per rank and step
+    px = vpr * px
+    exchange = (world > 1 and args.parallel == "exchange") or rig
     mv = MultiViewStep(model) if (world > 1 and not exchange) else None
     ex = None
     if exchange:
-        # Gaussian-sharded front/back end + all-to-all of splats (adgs_b200/parallel.py:SplatExchangeStep)
+        # Gaussian-sharded front/back end + exchange of splats (adgs_b200/parallel.py:SplatExchangeStep); a camera
+        # rig on one GPU is the same machinery at world size 1 (all views of the step in the multi-view kernels)
         from adgs_b200.parallel import SplatExchangeStep
-        shard = model.shard(rank, world)
-        model_full = model
+        shard = model.shard(rank, world) if world > 1 else model
         ex = SplatExchangeStep(shard)
         all_views = []
         for r in range(world):
-            c_r, t_r, f_r = view_for_rank(wl, r, device)
-            all_views.append((c_r, f_r))
+            for c_r, t_r, f_r in views_of_step(wl, r, device):
+                all_views.append((c_r, f_r))
         cot_dict = {"color": cot["color"], "depth": cot["depth"], "opacity": cot["opacity"], "flow": cot["flow"],
                     "semantic": cot["semantic"]}
-        del model_full
 
     def step():
         if ex is not None:
-            ex.run(all_views, lambda v, r: cot_dict, pipe)
+            ex.run(all_views, lambda v, r: cot_dict, pipe, views_per_rank=vpr)
             return None
         if mv is None:
             for p in params:
@@ -325,24 +369,59 @@ def run_ours(args):
         stage_ms = {lib.adgs_profile_stage_name(i).decode(): ms_buf[i] / prof_steps for i in range(ns)}
         R = int(getattr(model, "_last_num_rendered", R))
         if ex is not None:
-            R = max(0, int((ex._capacity - 65536) / 1.3))
-        total_b, per_stage = algorithmic_bytes(n_scene, n_obj, R, px)
+            R = max(0, int((ex._capacity - 65536) / 1.3)) * vpr      # the arena bound tracks the largest single view
+        total_b, per_stage = algorithmic_bytes(vpr * n_scene, vpr * n_obj, R, px)
         peak, peak_src = measured_hbm_peak()
         kernel_stages = {k: stage_ms[k] for k in ("per_gaussian_forward", "blend_forward", "blend_backward",
                                                    "per_gaussian_backward")}
         top = max(kernel_stages, key=kernel_stages.get)
         ach = per_stage[top] / (kernel_stages[top] * 1e-3) / 1e9
-        traffic = None
+        # per-launch DRAM bytes and warp instructions of each kernel from the committed `ncu --set full` capture of this
+        # same workload (profiles/traffic.json); they scale with the views of a step
+        captured = {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(top)
+                captured = json.load(open(tpath))
             except Exception:
-                traffic = None
+                captured = {}
+        same_wl = captured.get("_workload") == args.workload
+        sm_mhz = 1965.0
+        try:
+            sm_mhz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"])
+        except Exception:
+            pass
+        issue_peak = 148 * 4 * sm_mhz * 1e6          # warp instructions / s: 4 schedulers per SM, one issue per clock
+
+        def kernel_roofline(k):
+            c = captured.get(k) if same_wl else None
+            t = kernel_stages[k] * 1e-3
+            out = {"ms": round(kernel_stages[k], 4), "algorithmic_bytes": per_stage[k],
+                   "hbm_frac_algorithmic": round(per_stage[k] / t / 1e9 / peak, 4)}
+            if isinstance(c, dict):
+                if c.get("dram_bytes"):
+                    out["dram_bytes"] = c["dram_bytes"]
+                    out["hbm_frac_measured_traffic"] = round(c["dram_bytes"] / t / 1e9 / peak, 4)
+                if c.get("warp_instructions"):
+                    out["warp_instructions"] = c["warp_instructions"]
+                    out["issue_min_ms"] = round(c["warp_instructions"] / issue_peak * 1e3, 4)
+                    out["issue_frac"] = round(c["warp_instructions"] / issue_peak / t, 4)
+            return out
+
+        per_kernel = {k: kernel_roofline(k) for k in kernel_stages}
+        traffic = per_kernel[top].get("dram_bytes")
         roof = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": per_stage[top], "kernel_ms": round(kernel_stages[top], 4),
-                "note": "blend kernels are FP32/SFU-issue bound, not HBM bound (DESIGN.md); reported against HBM per BASELINE"}
+                "issue": {"peak_warp_instructions_per_s": issue_peak, "sm_mhz": sm_mhz,
+                          "warp_instructions": per_kernel[top].get("warp_instructions"),
+                          "min_ms_at_one_issue_per_clock": per_kernel[top].get("issue_min_ms"),
+                          "frac": per_kernel[top].get("issue_frac"),
+                          "note": "the blend kernels are bound by issue slots, not by HBM (DESIGN.md section 4): "
+                                  "frac = warp instructions (ncu capture in profiles/) / (148 SMs x 4 schedulers x clock) "
+                                  "/ measured kernel time"},
+                "per_kernel": per_kernel,
+                "note": "reported against HBM per BASELINE; `issue` is the bound that actually binds the blend kernels"}
         step_ach = total_b / (ms * 1e-3) / 1e9
         step_roof = {"algorithmic_bytes_per_view": total_b, "achieved_GBps": round(step_ach, 1),
                      "frac_of_hbm_peak": round(step_ach / peak, 4), "num_rendered": R}
@@ -354,8 +433,9 @@ def run_ours(args):
     H, W = wl["H"], wl["W"]
     hc = make_cotangents(wl, device, pinned=False)
     host_cot = torch.cat([hc[k].cpu().reshape(-1) for k in ("color", "depth", "opacity", "flow", "semantic")]).pin_memory()
-    host_cam = torch.cat([cam.world_view_transform.cpu().reshape(-1), cam.full_proj_transform.cpu().reshape(-1),
-                          cam.camera_center.cpu().reshape(-1)]).pin_memory()
+    cam_e2e = all_views[rank * vpr][0] if ex is not None else cam
+    host_cam = torch.cat([cam_e2e.world_view_transform.cpu().reshape(-1), cam_e2e.full_proj_transform.cpu().reshape(-1),
+                          cam_e2e.camera_center.cpu().reshape(-1)]).pin_memory()
     h2d = host_cot.numel() * 4 + host_cam.numel() * 4
     d2h = 4
 
@@ -418,9 +498,9 @@ def run_ours(args):
         torch.cuda.current_stream(device).wait_event(cam_ready)
         dcam.record_stream(torch.cuda.current_stream(device))
         views_ = list(all_views)
-        views_[rank] = (cam._replace(world_view_transform=dcam[0:16].view(4, 4),
-                                     full_proj_transform=dcam[16:32].view(4, 4), camera_center=dcam[32:35]),
-                        all_views[rank][1])
+        views_[rank * vpr] = (all_views[rank * vpr][0]._replace(world_view_transform=dcam[0:16].view(4, 4),
+                                                                full_proj_transform=dcam[16:32].view(4, 4),
+                                                                camera_center=dcam[32:35]), all_views[rank * vpr][1])
         box = {}
 
         def cots(v, r):
@@ -429,7 +509,7 @@ def run_ours(args):
             box["res"] = r
             return split_cot(flat)
 
-        ex.run(views_, cots, pipe)
+        ex.run(views_, cots, pipe, views_per_rank=vpr)
         read_metric(box["res"]["img_opacity"].mean())
 
     def e2e_step():
@@ -660,6 +740,20 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline()
 
+    # ---- the other BASELINE configs that fit one GPU, measured by the same harness (short runs; the headline stays
+    #      `value` above): configs[2] as a real 3-camera step, configs[4] the 10 M-Gaussian stress frame --------------
+    others = None
+    if world == 1 and args.workload == "kitti-375x1242-1M" and not args.no_other_workloads:
+        del model, params
+        torch.cuda.empty_cache()
+        others = {}
+        for name in ("waymo-3cam-1066x1600-3M", "stress-1920x1280-10M"):
+            try:
+                others[name] = measure_workload(name, device, steps=10, warmup=3)
+            except Exception as exc:
+                others[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
+
     if rank == 0 and ex is not None and ex.timing_report():
         print("exchange phases (ms):", ex.timing_report(), file=sys.stderr)
     if rank == 0:
@@ -667,22 +761,85 @@ def run_ours(args):
             "metric": METRIC, "value": round(mpix, 2), "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "views_per_step": world, "image": [wl["H"], wl["W"]],
-                       "gaussians": wl["n"], "object_fraction": wl["obj_frac"], "control_points": 32,
-                       "bspline_order": 5, "fourier_terms": 6, "sh_degree": 3, "flow": True, "objmask": True,
-                       "inv_depth": True, "l2": "inputs (>1.5 GB of parameters per step) exceed the 126 MB L2",
-                       "parallelism": (f"{world} rank(s); Gaussians sharded, views blended one per rank, NCCL all-to-all of "
-                                       "76-byte splats / 64-byte gradient records (no gradient all-reduce)" if exchange else
-                                       f"views sharded over {world} rank(s), flat-buffer NCCL all-reduce of parameter gradients")},
+            "config": make_config(args.workload, wl, world, vpr),
+            "parallelism_note": ((f"{world} rank(s); Gaussians sharded, every view blended on one rank; splats and 64-byte "
+                                  f"gradient records exchanged through {ex.exchange if world > 1 else 'local'} memory "
+                                  "(no gradient all-reduce)") if exchange else
+                                 f"views sharded over {world} rank(s), flat-buffer NCCL all-reduce of parameter gradients"),
             "gaussians_per_s": round(gauss, 1),
             "e2e": e2e, "gpu_launches": round(launches, 1), "clocks": clocks,
             "roofline": roof, "step_roofline": step_roof, "stage_ms": {k: round(v, 4) for k, v in (stage_ms or {}).items()},
             "cpu_baseline": cpu_base, "optimizer_step": adam, "loss_front_end": loss_fe, "train_iteration": train_it,
-            "densification": densify,
+            "densification": densify, "other_workloads": others,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_workload(name, device, steps=10, warmup=3):
+    """One workload on one GPU through the public API: value (inputs resident in HBM), per-stage CUDA-event times,
+    whole-step algorithmic-byte roofline. A camera rig runs all its cameras per step (multi-view kernels)."""
+    import ctypes as C
+    import torch
+    from adgs_b200 import _lib as L
+    from adgs_b200.gaussian_renderer import render
+    lib = L.load()
+    wl = WORKLOADS[name]
+    model, n_scene, n_obj = build_ours(wl, device)
+    views = views_of_step(wl, 0, device)
+    vpr = len(views)
+    cot = make_cotangents(wl, device)
+    pipe = SimpleNamespace(inv_depth=True, debug=False, sync_free=True)
+    params = model.hot_parameters()
+    px = vpr * wl["W"] * wl["H"]
+    ex = None
+    if vpr > 1:
+        from adgs_b200.parallel import SplatExchangeStep
+        ex = SplatExchangeStep(model)
+        ex_views = [(c, f) for c, t, f in views]
+
+    def step():
+        if ex is not None:
+            ex.run(ex_views, lambda v, r: cot, pipe, views_per_rank=vpr)
+            return
+        for p in params:
+            p.grad = None
+        cam, t, flow_t = views[0]
+        res = render(cam, model, None, pipe, flow_pkg=[flow_t, None, None, None, None, None], render_objmask=True)
+        torch.autograd.backward((res["render"], res["depth"], res["img_opacity"], res["img_flow"], res["img_semantic"]),
+                                (cot["color"], cot["depth"][0], cot["opacity"][0], cot["flow"], cot["semantic"]))
+
+    for _ in range(max(warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ns = lib.adgs_profile_num_stages()
+    ms_buf, cnt_buf = (C.c_float * ns)(), (C.c_int32 * ns)()
+    lib.adgs_profile_begin()
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    lib.adgs_profile_end(ms_buf, cnt_buf)
+    stage_ms = {lib.adgs_profile_stage_name(i).decode(): round(ms_buf[i] / 3, 4) for i in range(ns)}
+    if ex is not None:
+        R = max(0, int((ex._capacity - 65536) / 1.3)) * vpr
+    else:
+        R = int(getattr(model, "_last_num_rendered", 0))
+    total_b, _ = algorithmic_bytes(vpr * n_scene, vpr * n_obj, R, px)
+    peak, _src = measured_hbm_peak()
+    ach = total_b / (ms * 1e-3) / 1e9
+    return {"metric": METRIC, "value": round(px / (ms * 1e-3) / 1e6, 2), "unit": "Mpix/s", "ms_per_step": round(ms, 4),
+            "steps": steps, "config": make_config(name, wl, 1, vpr),
+            "gaussians_per_s": round(vpr * wl["n"] / (ms * 1e-3), 1), "num_rendered": R, "stage_ms": stage_ms,
+            "step_roofline": {"algorithmic_bytes_per_step": total_b, "achieved_GBps": round(ach, 1),
+                              "frac_of_hbm_peak": round(ach / peak, 4)}}
 
 
 def cpu_baseline(budget_s=15.0):
@@ -722,87 +879,197 @@ def cpu_baseline(budget_s=15.0):
 
 
 def run_reference(args):
-    """Reference arm: the reference's own implementation of the path -- its UNMODIFIED CUDA
-    rasterizer (oracle/_ref, compiled from /root/reference) driven by the torch trajectory exactly as
-    gaussian_renderer.render() drives it -- on the same workload, metric and timing harness.
-    (The reference has no CPU rasterizer; if neither a GPU nor oracle/_ref is available, the numpy
-    oracle port is timed on a bounded sample instead.)"""
+    """Reference arm: the reference's own implementation of the path -- its UNMODIFIED CUDA rasterizer (oracle/_ref,
+    compiled from /root/reference by oracle/Makefile) driven by the torch trajectory exactly as
+    gaussian_renderer.render() drives it (oracle/ref_pipeline.py) -- on the same workload, metric and timing harness.
+    The reference has no CPU rasterizer, so its implementation of the path IS this GPU one; it is the number to beat.
+    N > 1 (B-REF-N of BASELINE.md): the reference has no distributed code, so N ranks each hold a full replica, render
+    their own view of the batch and sum the parameter gradients with a plain torch.distributed.all_reduce -- the
+    'naive data parallel' curve. If neither a GPU nor oracle/_ref is available, the numpy oracle port is timed on a
+    bounded sample instead."""
     rank, world, local = dist_env()
-    if rank != 0:
-        return
     import torch
     from oracle import ref_module as REF
     wl = WORKLOADS[args.workload]
-    px = wl["W"] * wl["H"]
     cores = os.cpu_count() or 1
-    if torch.cuda.is_available() and REF.available():
-        from oracle import trajectory_oracle as TO
-        from oracle.ref_pipeline import reference_render
-        from adgs_b200 import scenes
-        torch.cuda.set_device(local)
-        device = torch.device("cuda", local)
-        n, n_obj = wl["n"], int(wl["n"] * wl["obj_frac"])
-        n_scene = n - n_obj
-        cam0 = scenes.make_camera(wl["W"], wl["H"], 90.0, time=T_CAMERA)
-        cloud = scenes.random_cloud(n, cam0, seed=0, median_radius_px=wl["median_radius_px"], cluster=wl.get("cluster"))
-        tensors = scenes.random_model_tensors(n_scene, n_obj, scenes.BENCH_ORDER_ARGS, cloud, seed=1, device=device)
-        for k, v in tensors.items():
-            if k != "gs_time":
-                v.requires_grad_(True)
-        ref = TO.ReferenceModel(scenes.BENCH_ORDER_ARGS, True, **tensors)
-        cam, t, flow_t = view_for_rank(wl, 0, device)
-        c = dict(cam=cam, W=wl["W"], H=wl["H"], n=n, background=torch.zeros(3, device=device),
-                 tan_fovx=math.tan(cam.FoVx * 0.5), tan_fovy=math.tan(cam.FoVy * 0.5), degree=3, inv_depth=True)
-        cot = make_cotangents(wl, device)
-        params = [getattr(ref, f) for f in ref.trainable()]
+    if not (torch.cuda.is_available() and REF.available()):
+        if rank == 0:
+            print(json.dumps(reference_port_line(args, cores)))
+        return
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    res = reference_measure(args.workload, rank, world, device, args.steps, max(args.warmup, 3), stage_split=True)
+    others = None
+    if world == 1 and args.workload == "kitti-375x1242-1M" and not args.no_other_workloads:
+        others = {}
+        for name in ("waymo-3cam-1066x1600-3M", "stress-1920x1280-10M"):
+            try:
+                r = reference_measure(name, 0, 1, device, 3, 3, stage_split=False)
+                others[name] = {"metric": METRIC, "value": r["value"], "unit": "Mpix/s", "ms_per_step": r["ms"],
+                                "steps": 3, "config": make_config(name, WORKLOADS[name], 1, r["vpr"])}
+            except Exception as exc:
+                others[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            torch.cuda.empty_cache()
+    blocking = None
+    if rank == 0 and world == 1 and not args.launch_blocking_child and args.workload == "kitti-375x1242-1M":
+        # train.py:277 sets CUDA_LAUNCH_BLOCKING=1 for training: how the reference actually runs. Must be set before
+        # CUDA initialises, hence a child process (5 steps).
+        try:
+            env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1")
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "5",
+                                  "--warmup", "3", "--workload", args.workload, "--launch-blocking-child",
+                                  "--no-other-workloads"], env=env, capture_output=True, text=True, timeout=300)
+            blocking = json.loads(out.stdout.strip().splitlines()[-1])["ms_per_step"]
+        except Exception as exc:
+            blocking = f"{type(exc).__name__}: {exc}"
+    if rank == 0:
+        value = res["value"]
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": res["ms"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": make_config(args.workload, wl, world, res["vpr"]),
+                "parallelism_note": ("full replica per rank, one view each, torch.distributed.all_reduce of every parameter "
+                                     "gradient (the reference itself is single-GPU: train.py:55-61)" if world > 1 else
+                                     "single GPU, one view per iteration like train.py"),
+                "gaussians_per_s": round(world * res["vpr"] * wl["n"] / (res["ms"] * 1e-3), 1),
+                "stage_ms": res["stages"], "ms_per_step_with_CUDA_LAUNCH_BLOCKING": blocking,
+                "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": "reference",
+                                 "sample": "unmodified reference CUDA rasterizer (oracle/_ref) + torch trajectory on the "
+                                           "GPU, full workload; runs on the GPU because the reference has no CPU rasterizer"},
+                "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "other_workloads": others}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
-        def step():
+
+def reference_measure(workload, rank, world, device, steps, warmup, stage_split):
+    """ms/step of the reference pipeline for `workload` on this rank's views (max over ranks), and -- on request -- a
+    per-stage split measured with CUDA events in a separate, synchronised pass."""
+    import torch
+    import torch.distributed as dist
+    from oracle import ref_module as REF
+    from oracle import trajectory_oracle as TO
+    from oracle.ref_pipeline import reference_render
+    from adgs_b200 import scenes
+    wl = WORKLOADS[workload]
+    tensors, n_scene, n_obj = scene_tensors(wl, device)
+    for k, v in tensors.items():
+        if k != "gs_time":
+            v.requires_grad_(True)
+    ref = TO.ReferenceModel(scenes.BENCH_ORDER_ARGS, True, **tensors)
+    views = views_of_step(wl, rank, device)
+    vpr = len(views)
+    px = vpr * wl["W"] * wl["H"]
+    cot = make_cotangents(wl, device)
+    params = [getattr(ref, f) for f in ref.trainable()]
+    cots = (cot["color"], cot["depth"], cot["opacity"], cot["flow"], cot["semantic"])
+
+    def case(cam):
+        return dict(cam=cam, W=wl["W"], H=wl["H"], n=wl["n"], background=torch.zeros(3, device=device),
+                    tan_fovx=math.tan(cam.FoVx * 0.5), tan_fovy=math.tan(cam.FoVy * 0.5), degree=3, inv_depth=True)
+
+    cases = [case(cam) for cam, _, _ in views]
+
+    def step():
+        for p in params:
+            p.grad = None
+        for c, (cam, t, flow_t) in zip(cases, views):       # one view per iteration, gradients accumulate
+            (color, radii, depth, opac, flow, sem), _ = reference_render(ref, c, t, flow_t, REF)
+            torch.autograd.backward((color, depth, opac, flow, sem), cots)
+        if world > 1:
+            for p in params:
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        tt = torch.tensor([ms], device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    stages = None
+    if stage_split and rank == 0:
+        # where the reference's step goes: its ATen trajectory, its rasterizer kernels, autograd through the trajectory
+        # (a separate pass with a device synchronisation between the stages; not part of `value`)
+        acc = {"trajectory_forward": 0.0, "rasterizer_forward": 0.0, "rasterizer_backward": 0.0,
+               "trajectory_backward_autograd": 0.0}
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        reps = 3
+        from oracle.ref_pipeline import RefRasterize
+        for _ in range(reps):
             for p in params:
                 p.grad = None
-            (color, radii, depth, opac, flow, sem), _ = reference_render(ref, c, t, flow_t, REF)
-            torch.autograd.backward((color, depth, opac, flow, sem),
-                                    (cot["color"], cot["depth"], cot["opacity"], cot["flow"], cot["semantic"]))
+            c, (cam, t, flow_t) = cases[0], views[0]
+            torch.cuda.synchronize()
+            ev[0].record()
+            flow = ref.get_deformed_xyz(flow_t)
+            pkg = ref.get_deformed_pkg(t)
+            sem = ref.get_obj_mask().float()[..., None]
+            scaling = ref.get_scaling()
+            leaves = [x.detach().requires_grad_(True) for x in (pkg["xyz"], pkg["opacity"], scaling, pkg["rotation"],
+                                                                 pkg["shs"], flow)]
+            ev[1].record()
+            out = RefRasterize.apply(REF, c, leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], leaves[5], sem)
+            ev[2].record()
+            torch.autograd.backward((out[0], out[2], out[3], out[4], out[5]), cots)
+            ev[3].record()
+            torch.autograd.backward((pkg["xyz"], pkg["opacity"], scaling, pkg["rotation"], pkg["shs"], flow),
+                                    tuple(x.grad for x in leaves))
+            ev[4].record()
+            torch.cuda.synchronize()
+            for i, k in enumerate(acc):
+                acc[k] += ev[i].elapsed_time(ev[i + 1]) / reps
+        stages = {k: round(v, 4) for k, v in acc.items()}
+    del ref, tensors, params
+    torch.cuda.empty_cache()
+    return {"ms": round(ms, 4), "value": round(world * px / (ms * 1e-3) / 1e6, 3), "vpr": vpr, "stages": stages}
 
-        for _ in range(max(args.warmup, 3)):
-            step()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            step()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
-        value = px / (ms * 1e-3) / 1e6
-        kind, sample = "reference", ("unmodified reference CUDA rasterizer (oracle/_ref) + torch trajectory on the GPU, "
-                                     "full workload; runs on the GPU because the reference has no CPU rasterizer")
-    else:
-        from oracle import raster_oracle as O
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import helpers as Hh
-        c = Hh.make_case(n=2000, W=96, H=64, seed=1, device="cpu")
-        s = Hh.oracle_settings(c)
-        n_ = Hh.to_np
-        cot = Hh.cotangents(c, device="cpu")
-        t0 = time.perf_counter()
-        k = 0
-        while k < args.steps and time.perf_counter() - t0 < 60:
-            out, st = O.rasterize_forward(s, n_(c["means3D"]), n_(c["opacity"]), n_(c["scales"]), n_(c["rotations"]),
-                                          None, n_(c["sh"]), None, n_(c["flow_points"]), n_(c["semantic"]))
-            O.rasterize_backward(s, st, out, n_(c["means3D"]), n_(cot["color"]), n_(cot["depth"]), n_(cot["flow"]),
-                                 n_(cot["semantic"]), n_(cot["opacity"]), n_(c["scales"]), n_(c["rotations"]), None,
-                                 n_(c["sh"]), n_(c["flow_points"]), n_(c["semantic"]))
-            k += 1
-        ms = (time.perf_counter() - t0) / max(k, 1) * 1e3
-        value = 96 * 64 / (ms * 1e-3) / 1e6
-        kind, sample = "port", "numpy oracle port on the host, bounded sample: 2000 Gaussians at 96x64 (rasterizer only)"
-    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mpix/s", "n_gpus": args.gpus,
+
+def reference_port_line(args, cores):
+    """No GPU / no oracle/_ref: the numpy oracle port of the rasterizer on a bounded sample."""
+    from oracle import raster_oracle as O
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as Hh
+    c = Hh.make_case(n=2000, W=96, H=64, seed=1, device="cpu")
+    s = Hh.oracle_settings(c)
+    n_ = Hh.to_np
+    cot = Hh.cotangents(c, device="cpu")
+    t0 = time.perf_counter()
+    k = 0
+    while k < args.steps and time.perf_counter() - t0 < 60:
+        out, st = O.rasterize_forward(s, n_(c["means3D"]), n_(c["opacity"]), n_(c["scales"]), n_(c["rotations"]),
+                                      None, n_(c["sh"]), None, n_(c["flow_points"]), n_(c["semantic"]))
+        O.rasterize_backward(s, st, out, n_(c["means3D"]), n_(cot["color"]), n_(cot["depth"]), n_(cot["flow"]),
+                             n_(cot["semantic"]), n_(cot["opacity"]), n_(c["scales"]), n_(c["rotations"]), None,
+                             n_(c["sh"]), n_(c["flow_points"]), n_(c["semantic"]))
+        k += 1
+    ms = (time.perf_counter() - t0) / max(k, 1) * 1e3
+    value = round(96 * 64 / (ms * 1e-3) / 1e6, 3)
+    wl = WORKLOADS[args.workload]
+    return {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload},
-            "cpu_baseline": {"value": round(value, 3), "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample},
-            "e2e": {"value": round(value, 3), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+            "config": make_config(args.workload, wl, 1, 1),
+            "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": "port",
+                             "sample": "numpy oracle port on the host, bounded sample: 2000 Gaussians at 96x64 (rasterizer only)"},
+            "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 
 def main():
@@ -813,6 +1080,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti-375x1242-1M", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true",
+                    help="skip the short runs of the other BASELINE configs (waymo 3-camera, stress 10M) at N=1")
+    ap.add_argument("--launch-blocking-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--e2e-blocking", action="store_true", help="e2e: block on the metric read before queuing the next step")
     ap.add_argument("--parallel", default="exchange", choices=["exchange", "allreduce"],
                     help="multi-GPU data path (N > 1): splat exchange (default) or replicated model + gradient all-reduce")

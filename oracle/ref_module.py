@@ -59,6 +59,15 @@ def load():
     return _lib
 
 
+def _join_default_stream(dev):
+    """The reference launches on the legacy default stream (stream 0), which is also torch's default stream: kernels
+    queued by torch before / after the call are ordered with it without any host synchronisation -- exactly like
+    the stock binding, whose only host block is the 4-byte num_rendered read (rasterizer_impl.cu:288). Only a caller
+    running torch on a NON-default stream needs an explicit join."""
+    if torch.cuda.current_stream(dev).cuda_stream != 0:
+        torch.cuda.synchronize(dev)
+
+
 def _p(t):
     if t is None or t.numel() == 0:
         return C.c_void_p(None)
@@ -100,7 +109,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
      projmatrix, campos) = keep
     rendered = 0
     if P != 0:
-        torch.cuda.synchronize(dev)   # the reference launches on the legacy default stream
+        _join_default_stream(dev)
         with torch.cuda.device(dev):
             rendered = lib.ref_forward(
                 cbs[0], cbs[1], cbs[2], None, C.c_int(P), C.c_int(int(degree)), C.c_int(M), C.c_int(D_S),
@@ -109,7 +118,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                 _p(viewmatrix), _p(projmatrix), _p(campos), C.c_float(tan_fovx), C.c_float(tan_fovy),
                 C.c_int(int(prefiltered)), _p(out_color), _p(out_depth), _p(img_opacity), _p(img_flow),
                 _p(img_semantic), C.c_int(int(inv_depth)), _p(radii), C.c_int(int(debug)))
-        torch.cuda.synchronize(dev)
+        _join_default_stream(dev)
         if rendered < 0:
             raise RuntimeError("reference forward failed")
     e = torch.empty((0,), dtype=torch.uint8, device=dev)
@@ -149,7 +158,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
      campos, radii, dL_dout_color, dL_dout_depth, dL_dout_flow, dL_dout_semantic, grad_img_opacity,
      img_opacity) = keep
     if P != 0:
-        torch.cuda.synchronize(dev)
+        _join_default_stream(dev)
         with torch.cuda.device(dev):
             st = lib.ref_backward(
                 C.c_int(P), C.c_int(int(degree)), C.c_int(M), C.c_int(int(R)), C.c_int(D_S), _p(background),
@@ -160,7 +169,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rot
                 _p(dL_dmeans2D), _p(dL_dconic), _p(dL_dopacity), _p(dL_dcolors), _p(dL_ddepths), _p(dL_dmeans3D),
                 _p(dL_dcov3D), _p(dL_dsh), _p(dL_dscales), _p(dL_drotations), _p(dL_dflow), _p(dL_dsem),
                 _p(grad_img_opacity), _p(img_opacity), C.c_int(int(inv_depth)), C.c_int(int(debug)))
-        torch.cuda.synchronize(dev)
+        _join_default_stream(dev)
         if st != 0:
             raise RuntimeError("reference backward failed")
     return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,

@@ -68,6 +68,16 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert lib.adgs_rasterize_backward(None, None, None, None, 0, None, None, None, None, None, None, None) == -1
 
 
+def test_more_than_2_pow_30_instances_is_refused_not_wrapped():
+    """The CUB-free sort's look-back words carry a 30-bit count (adgs_b200/csrc/sort.cu); the reference's 64-bit
+    sort (rasterizer_impl.cu:310-315) is valid to 2^32. Beyond 2^30 the library must say so, before any CUDA call."""
+    lib = L.load()
+    assert lib.adgs_sort_pairs(None, None, None, None, 1 << 30, 0, 32, None, None) == -4
+    assert lib.adgs_status_string(-4) == b"unsupported configuration"
+    assert lib.adgs_rasterize_forward_async(None, None, None, None, None, 1 << 30, None, None) == -4
+    assert lib.adgs_rasterize_forward_async(None, None, None, None, None, (1 << 30) - 1, None, None) == -1
+
+
 def test_densify_and_knn_reject_bad_arguments_without_a_gpu():
     """Argument validation of the densification / K-NN entry points returns before any CUDA call."""
     lib = L.load()

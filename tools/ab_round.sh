@@ -8,7 +8,7 @@ i=0
 for envs in "$@"; do
   [ "$envs" = "-" ] && envs=""
   name=$(echo "${envs:-default}" | tr ' =' '__')
-  env $envs timeout 300 python bench.py --no-cpu-baseline --steps 100 --warmup 10 > $OUT/bench_$name.jsonl 2> $OUT/bench_$name.err
+  env $envs timeout 300 python bench.py --no-cpu-baseline --no-other-workloads --steps 100 --warmup 10 > $OUT/bench_$name.jsonl 2> $OUT/bench_$name.err
   python - "$OUT/bench_$name.jsonl" "${envs:-default}" <<'PY'
 import json, sys
 try:

@@ -4,7 +4,7 @@ TAG=$1; KRE=$2; shift 2
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 name=$(echo "${*:-default}" | tr ' =' '__')
 env "$@" timeout 600 ncu --set full --clock-control none --import-source on -k regex:"$KRE" --launch-skip 6 --launch-count 1 \
-  -o $OUT/full_$name -f python bench.py --no-cpu-baseline --steps 2 --warmup 3 > $OUT/ncu_$name.log 2>&1
+  -o $OUT/full_$name -f python bench.py --no-cpu-baseline --no-other-workloads --steps 2 --warmup 3 > $OUT/ncu_$name.log 2>&1
 ncu -i $OUT/full_$name.ncu-rep --page raw --csv > $OUT/raw_$name.csv 2>/dev/null
 python - "$OUT/raw_$name.csv" <<'PY'
 import csv, sys
