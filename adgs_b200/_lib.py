@@ -284,6 +284,7 @@ SIGNATURES = {
                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, _P(ImageGrads),
                                        _P(Model), C.c_void_p, C.c_void_p, C.c_void_p]),
     "adgs_shard_state_bytes": (C.c_size_t, [C.c_int32]),
+    "adgs_shard_state_radii_offset": (C.c_size_t, [C.c_int32]),
     "adgs_shard_forward": (C.c_int, [_P(Camera), _P(Model), _P(TimeBasis), C.c_int32, _P(Splats), C.c_void_p,
                                      C.c_void_p]),
     "adgs_splats_forward": (C.c_int, [_P(Camera), _P(Splats), C.c_int32, C.c_int32, _P(Images), C.c_void_p, C.c_void_p,

@@ -602,6 +602,7 @@ int validate_model(const adgs_model* m, const adgs_time_basis* tb)
 // backward sums the per-view contributions in registers and writes every dense gradient once.
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxViews = 8;
+constexpr int kGradRing = 4;  // views of gradient records in flight in the multi-view backward
 
 struct ViewIO {
     adgs_time_basis tb;
@@ -616,6 +617,7 @@ struct ViewIO {
     float* cov3D;
     uint8_t* clamped;
     float4* saved;
+    int32_t* radii_state;      // owner-side copy of the radii inside the shard state (forward writes, backward reads)
     float* mean_x;             // optional planes of the pixel-space means (splat exchange)
     float* mean_y;
     const float* grad_record;  // backward only
@@ -634,7 +636,9 @@ struct MultiViewArgs {
     ViewIO v[kMaxViews];
 };
 
-template <int TPB, int MINB>
+// SPLIT: blockIdx.y selects ONE view per CTA (as many threads as the single-GPU kernel has, every CTA's stores going
+// to one destination); otherwise each thread loops over all views and reads its parameters once.
+template <int TPB, int MINB, bool SPLIT>
 __global__ void __launch_bounds__(TPB, MINB) shard_forward_multi_kernel(const __grid_constant__ MultiViewArgs a)
 {
     __shared__ CamSmem cam;
@@ -670,7 +674,8 @@ __global__ void __launch_bounds__(TPB, MINB) shard_forward_multi_kernel(const __
     }
     const float dc0[3] = {sh[0], sh[1], sh[2]};
 
-    for (int vi = 0; vi < a.num_views; ++vi) {
+    const int v_begin = SPLIT ? (int)blockIdx.y : 0, v_end = SPLIT ? (int)blockIdx.y + 1 : a.num_views;
+    for (int vi = v_begin; vi < v_end; ++vi) {
         const ViewIO& V = a.v[vi];
         const adgs_time_basis& tb = V.tb;
         __syncthreads();
@@ -736,10 +741,12 @@ __global__ void __launch_bounds__(TPB, MINB) shard_forward_multi_kernel(const __
         V.saved[(size_t)g * 3 + 2] = make_float4(dc[0], dc[1], dc[2], 0.f);
         if (!visible) {
             V.radii[g] = 0;
+            if (V.radii_state) V.radii_state[g] = 0;
             V.tiles_touched[g] = 0;
             V.depth_keys[g] = 0xFFFFFFFFu;
             continue;
         }
+        if (V.radii_state) V.radii_state[g] = sg.radius;
         if (V.mean_x) {
             V.mean_x[g] = sg.px;
             V.mean_y[g] = sg.py;
@@ -765,7 +772,7 @@ __global__ void __launch_bounds__(TPB, MINB) shard_forward_multi_kernel(const __
     }
 }
 
-template <int TPB, int MINB>
+template <int TPB, int MINB, bool RING>
 __global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const __grid_constant__ MultiViewArgs a)
 {
     __shared__ CamSmem cam;
@@ -804,6 +811,39 @@ __global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const _
     for (int v = 0; v < kMaxViews; ++v) ddc[v][0] = ddc[v][1] = ddc[v][2] = 0.f;
     float4 rot_scene = make_float4(1.f, 0.f, 0.f, 0.f);
 
+    // The gradient records of view v may live in ANOTHER GPU's memory (peer-memory exchange: every load is an NVLink
+    // round trip of a few microseconds), so they are requested ahead of their use:
+    //   RING  = cp.async into a ring of kGradRing views in shared memory, each thread fetching (and later reading)
+    //           only its own four quads; view v + kGradRing is requested as soon as view v has been consumed
+    //   !RING = the next view's four quads are loaded into registers before the current view's arithmetic
+    extern __shared__ float4 s_grad_ring[];  // [kGradRing][4][TPB] (RING only)
+    auto ring_slot = [&](int vi, int q) -> float4* { return s_grad_ring + ((vi % kGradRing) * 4 + q) * TPB + threadIdx.x; };
+    float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0, n2 = n0, n3 = n0;
+    auto request_view = [&](int vi) {
+        if (valid && vi < a.num_views) {
+            const float4* gr = reinterpret_cast<const float4*>(a.v[vi].grad_record) + (size_t)g * 4;
+            if (RING) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t d = (uint32_t)__cvta_generic_to_shared(ring_slot(vi, q));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gr + q) : "memory");
+                }
+            } else {
+                n0 = gr[0];
+                n1 = gr[1];
+                n2 = gr[2];
+                n3 = gr[3];
+            }
+        }
+        if (RING) asm volatile("cp.async.commit_group;" ::: "memory");  // one group per view, empty or not
+    };
+    if (RING) {
+#pragma unroll
+        for (int vi = 0; vi < kGradRing; ++vi) request_view(vi);
+    } else {
+        request_view(0);
+    }
+
 #pragma unroll
     for (int vi = 0; vi < kMaxViews; ++vi) {
         if (vi >= a.num_views) break;
@@ -813,15 +853,27 @@ __global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const _
         load_camera(cam, V.view, V.proj, V.campos, nullptr);
         const bool flow = tb.has_flow != 0;
         float dxt[3] = {0.f, 0.f, 0.f}, dfl[3] = {0.f, 0.f, 0.f};
+        float4 g0 = n0, g1 = n1, g2 = n2, g3 = n3;
+        if (RING) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(kGradRing - 1) : "memory");  // view vi has landed
+            if (valid) {
+                g0 = *ring_slot(vi, 0);
+                g1 = *ring_slot(vi, 1);
+                g2 = *ring_slot(vi, 2);
+                g3 = *ring_slot(vi, 3);
+            }
+            request_view(vi + kGradRing);
+        } else {
+            request_view(vi + 1);
+        }
+        const int radius = valid ? V.radii[g] : 0;
         if (valid) {
-            const float4* gr = reinterpret_cast<const float4*>(V.grad_record) + (size_t)g * 4;
-            const float4 g0 = gr[0], g1 = gr[1], g2 = gr[2], g3 = gr[3];
             if (V.dL_dmeans2D) {
                 V.dL_dmeans2D[3 * (size_t)g + 0] = g0.x;
                 V.dL_dmeans2D[3 * (size_t)g + 1] = g0.y;
                 V.dL_dmeans2D[3 * (size_t)g + 2] = 0.f;
             }
-            const bool visible = V.radii[g] > 0;
+            const bool visible = radius > 0;
             const float4 sv0 = V.saved[(size_t)g * 3 + 0];
             const float4 sv1 = V.saved[(size_t)g * 3 + 1];
             const float rot[4] = {sv1.x, sv1.y, sv1.z, sv1.w};
@@ -1501,22 +1553,31 @@ size_t adgs_shard_state_bytes(int32_t N)
 {
     // cov3D (6 floats) + clamped (1 byte) + saved (12 floats) per Gaussian of the shard, per view
     const size_t n = (size_t)(N > 0 ? N : 0);
-    return n * 6 * sizeof(float) + n + n * kSavedFloats * sizeof(float) + 3 * 128 + 256;
+    return n * 6 * sizeof(float) + n + n * kSavedFloats * sizeof(float) + n * sizeof(int32_t) + 4 * 128 + 256;
 }
 
 struct ShardState {
     float* cov3D;
     uint8_t* clamped;
     float4* saved;
+    int32_t* radii;  // the owner's copy of the radii (the splats' own copy may live in another GPU's memory)
     static ShardState from_chunk(char*& c, size_t N)
     {
         ShardState s;
         carve(c, s.cov3D, N * 6);
         carve(c, s.clamped, N);
         carve(c, s.saved, N * 3);
+        carve(c, s.radii, N);
         return s;
     }
 };
+
+size_t adgs_shard_state_radii_offset(int32_t N)
+{
+    char* c = nullptr;
+    ShardState s = ShardState::from_chunk(c, (size_t)(N > 0 ? N : 0));
+    return (size_t)s.radii;   // relative to a 128-byte aligned chunk base
+}
 
 int adgs_shard_forward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
                        int32_t render_objmask, const adgs_splats* out, char* shard_state, adgs_stream_t stream_)
@@ -1668,14 +1729,21 @@ int adgs_shard_forward_multi(int32_t num_views, const adgs_camera* cams, const a
         V.cov3D = ss.cov3D;
         V.clamped = ss.clamped;
         V.saved = ss.saved;
+        V.radii_state = ss.radii;
         V.mean_x = outs[v].mean_x;
         V.mean_y = outs[v].mean_y;
     }
     {
         StageScope sc(kStagePerGaussianFwd, stream);
-        // 2-GPU sweep r1l: 128 registers best; 4-GPU sweep r1p: a view-parallel grid (one CTA per chunk and view)
-        // was slower (0.175-0.192 ms vs 0.168 ms) and was dropped
-        shard_forward_multi_kernel<256, 2><<<(N + 255) / 256, 256, 0, stream>>>(a);
+        // ADGS_TUNE_MFWD: 0 = every thread loops over the views (parameters read once; best for a few large views,
+        // e.g. a camera rig on one GPU), 1 = one view per CTA (grid.y = views: the thread count of the single-GPU
+        // kernel when the model is sharded over as many ranks as there are views), -1 = pick by shard size
+        static const int variant = tune_variant("ADGS_TUNE_MFWD", -1);
+        const bool split = variant == 1 || (variant == -1 && num_views > 1 && (long long)N * num_views <= 2000000ll);
+        if (split)
+            shard_forward_multi_kernel<128, 8, true><<<dim3((N + 127) / 128, num_views), 128, 0, stream>>>(a);
+        else
+            shard_forward_multi_kernel<256, 2, false><<<(N + 255) / 256, 256, 0, stream>>>(a);
         count_launch(1);
     }
     return check_stage("shard forward (multi-view)", cams[0].debug != 0, stream);
@@ -1701,6 +1769,10 @@ int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cams, const 
     a.m = *model;
     a.g = *grads;
     a.num_views = num_views;
+    // accumulate: bit 0 = add into `grads` (later rounds of a batch); bit 1 = the caller has already zero-filled the
+    // control-point planes of grads->xyz_deform / rot_deform (e.g. on a side stream underneath the blend backward)
+    const bool planes_zeroed = (accumulate & 2) != 0;
+    accumulate &= 1;
     a.accumulate = accumulate;
     // scratch: per view dq (N_obj float4) + 32 floats of background sums
     char* sc = scratch;
@@ -1708,7 +1780,7 @@ int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cams, const 
         int st = validate_model(model, &bases[v]);
         if (st) return st;
         if ((st = check_render_args(&cams[v]))) return st;
-        if (!radii[v] || !shard_states[v] || !grad_records[v]) return ADGS_ERR_ARG;
+        if (!shard_states[v] || !grad_records[v]) return ADGS_ERR_ARG;
         char* c = shard_states[v];
         ShardState ss = ShardState::from_chunk(c, (size_t)N);
         ViewIO& V = a.v[v];
@@ -1717,19 +1789,21 @@ int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cams, const 
         V.view = cams[v].viewmatrix;
         V.proj = cams[v].projmatrix;
         V.campos = cams[v].campos;
-        V.radii = const_cast<int32_t*>(radii[v]);
+        V.radii = radii[v] ? const_cast<int32_t*>(radii[v]) : ss.radii;   // null: the copy adgs_shard_forward_multi kept
         V.cov3D = ss.cov3D;
         V.clamped = ss.clamped;
         V.saved = ss.saved;
         V.grad_record = grad_records[v];
         V.dL_dmeans2D = dL_dmeans2D ? dL_dmeans2D[v] : nullptr;
         carve(sc, V.dq_scratch, (size_t)(No > 0 ? No : 1));
-        carve(sc, V.bg_scratch, 32);
     }
+    float* bg_all = nullptr;  // the views' background sums in one block: one memset instead of one per view
+    carve(sc, bg_all, (size_t)32 * kMaxViews);
+    for (int v = 0; v < num_views; ++v) a.v[v].bg_scratch = bg_all + 32 * v;
     {
         StageScope scope(kStageFills, stream);
-        for (int v = 0; v < num_views; ++v) cudaMemsetAsync(a.v[v].bg_scratch, 0, 32 * sizeof(float), stream);
-        if (!accumulate && No > 0) {
+        cudaMemsetAsync(bg_all, 0, (size_t)32 * num_views * sizeof(float), stream);
+        if (!accumulate && !planes_zeroed && No > 0) {
             // windows differ between views and are accumulated with += : start from all-zero planes
             if (grads->xyz_deform && bases[0].xyz.n_cols > 0)
                 cudaMemsetAsync(grads->xyz_deform, 0, (size_t)bases[0].xyz.n_cols * 3 * No * sizeof(float), stream);
@@ -1741,7 +1815,15 @@ int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cams, const 
     {
         StageScope scope(kStagePerGaussianBwd, stream);
         // sweep r1l (2 GPUs): 168 registers 0.289 ms, 128 registers 0.244 ms, 230 registers 0.366 ms
-        shard_backward_multi_kernel<128, 4><<<(N + 127) / 128, 128, 0, stream>>>(a);
+        // ADGS_TUNE_MBWD: how the (possibly remote) gradient records are prefetched: 0 = next view into registers,
+        // 1 = cp.async ring of kGradRing views in shared memory, -1 = ring when there are more views than the ring holds
+        static const int variant = tune_variant("ADGS_TUNE_MBWD", -1);
+        const bool ring = variant == 1 || (variant == -1 && num_views > kGradRing);
+        if (ring)
+            shard_backward_multi_kernel<128, 4, true>
+                <<<(N + 127) / 128, 128, (size_t)kGradRing * 4 * 128 * sizeof(float4), stream>>>(a);
+        else
+            shard_backward_multi_kernel<128, 4, false><<<(N + 127) / 128, 128, 0, stream>>>(a);
         count_launch(1);
     }
     if ((st = check_stage("shard backward (multi-view)", debug, stream))) return st;
@@ -1769,7 +1851,8 @@ int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cams, const 
 
 size_t adgs_shard_scratch_bytes(int32_t num_views, int32_t N_obj)
 {
-    return (size_t)(num_views > 0 ? num_views : 1) * ((size_t)(N_obj > 0 ? N_obj : 1) * 16 + 128 + 256) + 256;
+    return (size_t)(num_views > 0 ? num_views : 1) * ((size_t)(N_obj > 0 ? N_obj : 1) * 16 + 128 + 256) + 256 +
+           (size_t)32 * kMaxViews * sizeof(float) + 128;
 }
 
 }  // extern "C"

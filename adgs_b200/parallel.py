@@ -229,7 +229,10 @@ class PeerBuffers:
                                                 stream), "peer_barrier")
 
     def local_radii(self):
-        return torch.as_tensor(_RawCudaArray(self.meta(self.rank, 2), (self.world * self.n,), "<i4"), device=self.device)
+        if "_local_radii" not in self.__dict__:
+            self._local_radii = torch.as_tensor(_RawCudaArray(self.meta(self.rank, 2), (self.world * self.n,), "<i4"),
+                                                device=self.device)
+        return self._local_radii
 
     def timed_out(self):
         return bool(torch.as_tensor(_RawCudaArray(self.status_ptr, (1,), "<u4"), device=self.device).item())
@@ -296,11 +299,16 @@ class SplatExchangeStep:
         s = GaussianRasterizationSettings(
             image_height=int(cam.image_height), image_width=int(cam.image_width),
             tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5),
-            bg=torch.zeros(3, device=dev), scale_modifier=1.0, viewmatrix=cam.world_view_transform.to(dev),
+            bg=self._zero_bg(dev), scale_modifier=1.0, viewmatrix=cam.world_view_transform.to(dev),
             projmatrix=cam.full_proj_transform.to(dev), sh_degree=self.model.active_sh_degree,
             campos=cam.camera_center.to(dev), prefiltered=False, inv_depth=getattr(pipe, "inv_depth", False),
             debug=getattr(pipe, "debug", False))
         return _camera(s, keep)
+
+    def _zero_bg(self, dev):
+        if "_bg" not in self.__dict__:
+            self._bg = torch.zeros(3, device=dev)
+        return self._bg
 
     def _all_to_all(self, send):
         """send: (G, ...) -> recv: (G, ...), chunk g goes to rank g."""
@@ -362,6 +370,7 @@ class SplatExchangeStep:
                 L.check(lib.adgs_shard_forward_multi(V, cam_arr, C.byref(cmodel), basis_arr, int(self.render_objmask),
                                                      splat_arr, state_arr, stream), "shard_forward_multi")
                 radii = meta[:, 2]
+                zeroed = self._zero_planes_async(dev) if first else False
                 mark("shard_forward")
                 # ---- splats travel to the rank that blends their view (chunk d of dim 0 -> rank d): the
                 #      20-byte binning state first, the 64-byte records behind it on the NCCL stream, so
@@ -467,10 +476,12 @@ class SplatExchangeStep:
                 radii_arr = (C.c_void_p * V)(*[radii[v].data_ptr() for v in range(V)])
                 grec_arr = (C.c_void_p * V)(*[r_grec[v].data_ptr() for v in range(V)])
                 d2_arr = (C.c_void_p * V)(*[d2[v].data_ptr() for v in range(V)])
+                if zeroed:
+                    torch.cuda.current_stream(dev).wait_stream(self._fill_stream)
                 L.check(lib.adgs_shard_backward_multi(V, cam_arr, C.byref(cmodel), basis_arr, radii_arr, state_arr,
-                                                      grec_arr, C.byref(gm), int(not first), d2_arr, L.ptr(scratch),
-                                                      stream), "shard_backward_multi")
-                first = False
+                                                      grec_arr, C.byref(gm), int(not first) | (2 if zeroed else 0),
+                                                      d2_arr, L.ptr(scratch), stream), "shard_backward_multi")
+                first, zeroed = False, False
                 mark("shard_backward")
                 for v in range(V):
                     stats.append((d2[v], radii[v]))
@@ -489,6 +500,19 @@ class SplatExchangeStep:
                 timing["count"] += 1
             timing["marks"] = []
         return results, stats
+
+    def _zero_planes_async(self, dev):
+        """Zero-fill of the control-point gradient planes (their B-spline windows differ between views, so the
+        per-Gaussian backward accumulates into them) on a side stream: pure HBM writes that run underneath the
+        issue-bound blend kernels instead of in front of the per-Gaussian backward."""
+        if "_fill_stream" not in self.__dict__:
+            self._fill_stream = torch.cuda.Stream(device=dev)
+        fs = self._fill_stream
+        fs.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(fs):
+            self.grads["xyz_deform"].zero_()
+            self.grads["rot_deform"].zero_()
+        return True
 
     def _resolve_checks(self):
         """Counters of earlier sync-free steps: grow the arena; an overflowed step was dropped on the device."""
@@ -573,6 +597,7 @@ class SplatExchangeStep:
                 cmodel = m.c_model()
                 L.check(lib.adgs_shard_forward_multi(G, cam_arr, C.byref(cmodel), basis_arr, int(self.render_objmask),
                                                      splat_arr, state_arr, stream), "shard_forward_multi")
+                zeroed = self._zero_planes_async(dev) if first else False
                 pb.barrier(stream)          # every rank's splats of my view have landed
                 cam, flow_t = batch[r]
                 cc = cams[r]
@@ -605,16 +630,20 @@ class SplatExchangeStep:
                 scratch = torch.empty((lib.adgs_shard_scratch_bytes(G, m.n_obj),), dtype=torch.uint8, device=dev)
                 gm = m.c_model_from(self.grads, with_time=False)
                 d2 = torch.empty((G, n, 3), **o)
-                radii_arr = (C.c_void_p * G)(*[pb.meta(v, 2, r) for v in range(G)])     # peer loads
-                grec_arr = (C.c_void_p * G)(*[pb.grec(v, r) for v in range(G)])         # peer loads
+                radii_arr = (C.c_void_p * G)()      # null: the radii copy the forward kept in the shard state
+                grec_arr = (C.c_void_p * G)(*[pb.grec(v, r) for v in range(G)])         # peer loads (cp.async ring)
                 d2_arr = (C.c_void_p * G)(*[d2[v].data_ptr() for v in range(G)])
+                if zeroed:
+                    torch.cuda.current_stream(dev).wait_stream(self._fill_stream)
                 L.check(lib.adgs_shard_backward_multi(G, cam_arr, C.byref(cmodel), basis_arr, radii_arr, state_arr,
-                                                      grec_arr, C.byref(gm), int(not first), d2_arr, L.ptr(scratch),
-                                                      stream), "shard_backward_multi")
-                first = False
+                                                      grec_arr, C.byref(gm), int(not first) | (2 if zeroed else 0),
+                                                      d2_arr, L.ptr(scratch), stream), "shard_backward_multi")
+                first, zeroed = False, False
+                roff = lib.adgs_shard_state_radii_offset(n)
                 for v in range(G):
-                    # radii of my Gaussians in view v: copied out of rank v's buffer (the next round overwrites it)
-                    stats.append((d2[v], torch.as_tensor(_RawCudaArray(pb.meta(v, 2, r), (n,), "<i4"), device=dev).clone()))
+                    # radii of my Gaussians in view v: the owner-side copy inside the (128-byte aligned) shard state
+                    off = (-state[v].data_ptr()) % 128 + roff
+                    stats.append((d2[v], state[v, off:off + 4 * n].view(torch.int32)))
         if self.grads["background_deform"].numel():
             dist.all_reduce(self.grads["background_deform"], op=dist.ReduceOp.SUM, group=self.group)
         for name in self.names:

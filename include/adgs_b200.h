@@ -360,6 +360,10 @@ typedef struct adgs_splats {
 } adgs_splats;
 
 ADGS_API size_t adgs_shard_state_bytes(int32_t N);
+/* byte offset, inside a 128-byte aligned shard-state chunk, of the int32 radii (N) that adgs_shard_forward_multi keeps
+ * for the owner of the Gaussians (the adgs_splats copy may live in the blending rank's memory); adgs_shard_backward_multi
+ * reads it when its radii[v] is null */
+ADGS_API size_t adgs_shard_state_radii_offset(int32_t N);
 ADGS_API int adgs_shard_forward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
                        int32_t render_objmask, const adgs_splats* out, char* shard_state, adgs_stream_t stream);
 ADGS_API int adgs_splats_forward(const adgs_camera* cam, const adgs_splats* splats, int32_t D_S, int32_t has_flow,
@@ -384,7 +388,9 @@ ADGS_API int adgs_shard_backward(const adgs_camera* cam, const adgs_model* model
 
 /* Multi-view variants (up to 8 views per call): ONE launch evaluates a shard for all views of a
  * round -- parameters are read once, the backward sums the views in registers and writes every dense
- * gradient once. Array arguments hold `num_views` entries. scratch: adgs_shard_scratch_bytes(). */
+ * gradient once. Array arguments hold `num_views` entries. scratch: adgs_shard_scratch_bytes().
+ * adgs_shard_backward_multi `accumulate`: bit 0 = add into `grads` (later rounds of a batch), bit 1 = the caller has
+ * already zero-filled grads->xyz_deform / rot_deform (their windows differ between views and are accumulated). */
 #define ADGS_MAX_VIEWS 8
 ADGS_API size_t adgs_shard_scratch_bytes(int32_t num_views, int32_t N_obj);
 ADGS_API int adgs_shard_forward_multi(int32_t num_views, const adgs_camera* cams, const adgs_model* model,
