@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(TPB, MINB) fused_forward_kernel(const __grid_c
     } else {
         qraw = reinterpret_cast<const float4*>(m.rotation)[g];
     }
-    const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+    const float qn = fmaxf(sqrtf(sumsq4_pinned(qraw.x, qraw.y, qraw.z, qraw.w)), 1e-12f);
     const float rot[4] = {qraw.x / qn, qraw.y / qn, qraw.z / qn, qraw.w / qn};
 
     // ---- opacity, scale ------------------------------------------------------------------
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
         // rotation
         if (!is_obj) {
             const float4 qraw = reinterpret_cast<const float4*>(m.rotation)[g];
-            const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+            const float qn = fmaxf(sqrtf(sumsq4_pinned(qraw.x, qraw.y, qraw.z, qraw.w)), 1e-12f);
             put4(reinterpret_cast<float4*>(a.g.rotation) + g,
                  normalize4_bwd(make_float4(rot[0], rot[1], rot[2], rot[3]), qn, make_float4(dq[0], dq[1], dq[2], dq[3])),
                  a.accumulate);
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(TPB, MINB) rotation_backward_kernel(const __gr
         qraw.z += r.y;
         qraw.w += r.z;
     }
-    const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+    const float qn = fmaxf(sqrtf(sumsq4_pinned(qraw.x, qraw.y, qraw.z, qraw.w)), 1e-12f);
     const float4 qhat = make_float4(qraw.x / qn, qraw.y / qn, qraw.z / qn, qraw.w / qn);
     const float4 graw = normalize4_bwd(qhat, qn, a.dq_scratch[j]);  // wxyz
     put4(reinterpret_cast<float4*>(a.g.rotation) + g, (tb.quat.n_ctrl == 0) ? graw : make_float4(0.f, 0.f, 0.f, 0.f),
@@ -643,6 +643,7 @@ __global__ void __launch_bounds__(TPB, MINB) shard_forward_multi_kernel(const __
 {
     __shared__ CamSmem cam;
     __shared__ float s_bg[6];
+    __shared__ float4 s_stage[TPB / 32][128];  // per warp: 32 records on their way out, coalesced (warp_store_records)
     const adgs_model& m = a.m;
     const int N = m.N_scene + m.N_obj;
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -689,7 +690,10 @@ __global__ void __launch_bounds__(TPB, MINB) shard_forward_multi_kernel(const __
             s_bg[threadIdx.x] = v;
         }
         load_camera(cam, V.view, V.proj, V.campos, nullptr);
-        if (!valid) continue;
+        float4 rq[4];  // this Gaussian's blend record (left zero if it is culled: never read, tiles_touched = 0)
+        rq[0] = rq[1] = rq[2] = rq[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        [&]() {
+        if (!valid) return;
         const bool flow = tb.has_flow != 0;
 
         float xt[3], xf[3];
@@ -710,7 +714,7 @@ __global__ void __launch_bounds__(TPB, MINB) shard_forward_multi_kernel(const __
             xf[d] += s_bg[3 + d];
         }
         const float4 qraw = is_obj ? object_rotation_raw(m, tb, g, j, nullptr, nullptr) : qscene;
-        const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+        const float qn = fmaxf(sqrtf(sumsq4_pinned(qraw.x, qraw.y, qraw.z, qraw.w)), 1e-12f);
         const float rot[4] = {qraw.x / qn, qraw.y / qn, qraw.z / qn, qraw.w / qn};
         float op = sig;
         if (is_obj && tb.use_time_mask) {
@@ -744,7 +748,7 @@ __global__ void __launch_bounds__(TPB, MINB) shard_forward_multi_kernel(const __
             if (V.radii_state) V.radii_state[g] = 0;
             V.tiles_touched[g] = 0;
             V.depth_keys[g] = 0xFFFFFFFFu;
-            continue;
+            return;
         }
         if (V.radii_state) V.radii_state[g] = sg.radius;
         if (V.mean_x) {
@@ -764,11 +768,16 @@ __global__ void __launch_bounds__(TPB, MINB) shard_forward_multi_kernel(const __
         c2[2] = make_float2(sg.cov3D[4], sg.cov3D[5]);
         const float dfeat = V.rp.inv_depth ? (1.0f / (sg.depth + 0.0000001f)) : sg.depth;
         const float sem0 = (a.render_objmask && is_obj) ? 1.f : 0.f;
-        store_blend_record(V.record + (size_t)g * 4, sg.px, sg.py, sg.conic_x, sg.conic_y, sg.conic_z, op, sg.depth, rgb,
-                           dfeat, flow ? xf[0] : 0.f, flow ? xf[1] : 0.f, flow ? xf[2] : 0.f, sem0);
+        make_blend_record(rq, sg.px, sg.py, sg.conic_x, sg.conic_y, sg.conic_z, op, sg.depth, rgb, dfeat,
+                          flow ? xf[0] : 0.f, flow ? xf[1] : 0.f, flow ? xf[2] : 0.f, sem0);
         V.radii[g] = sg.radius;
         V.tiles_touched[g] = sg.tiles;
         V.depth_keys[g] = __float_as_uint(sg.depth);
+        }();
+        // the records may live in another GPU's memory: the warp writes its 2 KB block with 512-byte instructions
+        const int warp_g0 = g - (int)(threadIdx.x & 31);
+        warp_store_records(V.record + (size_t)warp_g0 * 4, warp_g0 < N ? (size_t)(N - warp_g0) * 4 : 0, rq,
+                           s_stage[threadIdx.x >> 5]);
     }
 }
 
@@ -818,24 +827,26 @@ __global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const _
     //   !RING = the next view's four quads are loaded into registers before the current view's arithmetic
     extern __shared__ float4 s_grad_ring[];  // [kGradRing][4][TPB] (RING only)
     auto ring_slot = [&](int vi, int q) -> float4* { return s_grad_ring + ((vi % kGradRing) * 4 + q) * TPB + threadIdx.x; };
-    float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f), n1 = n0, n2 = n0, n3 = n0;
+    __shared__ float4 s_stage[TPB / 32][128];  // per warp: 32 records coming in, coalesced (warp_load_records_*)
+    const int warp_g0 = g - (int)(threadIdx.x & 31);
+    const size_t warp_quads = warp_g0 < N ? (size_t)(N - warp_g0) * 4 : 0;
+    float4 nr[4];  // !RING: the warp's next block, quad k of the block in lane k % 32 (coalesced), not yet transposed
+    nr[0] = nr[1] = nr[2] = nr[3] = make_float4(0.f, 0.f, 0.f, 0.f);
     auto request_view = [&](int vi) {
-        if (valid && vi < a.num_views) {
-            const float4* gr = reinterpret_cast<const float4*>(a.v[vi].grad_record) + (size_t)g * 4;
-            if (RING) {
+        if (RING) {
+            if (valid && vi < a.num_views) {
+                const float4* gr = reinterpret_cast<const float4*>(a.v[vi].grad_record) + (size_t)g * 4;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const uint32_t d = (uint32_t)__cvta_generic_to_shared(ring_slot(vi, q));
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gr + q) : "memory");
                 }
-            } else {
-                n0 = gr[0];
-                n1 = gr[1];
-                n2 = gr[2];
-                n3 = gr[3];
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");  // one group per view, empty or not
+        } else if (vi < a.num_views) {
+            warp_load_records_issue(reinterpret_cast<const float4*>(a.v[vi].grad_record) + (size_t)warp_g0 * 4, warp_quads,
+                                    nr);
         }
-        if (RING) asm volatile("cp.async.commit_group;" ::: "memory");  // one group per view, empty or not
     };
     if (RING) {
 #pragma unroll
@@ -853,7 +864,7 @@ __global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const _
         load_camera(cam, V.view, V.proj, V.campos, nullptr);
         const bool flow = tb.has_flow != 0;
         float dxt[3] = {0.f, 0.f, 0.f}, dfl[3] = {0.f, 0.f, 0.f};
-        float4 g0 = n0, g1 = n1, g2 = n2, g3 = n3;
+        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0, g3 = g0;
         if (RING) {
             asm volatile("cp.async.wait_group %0;" ::"n"(kGradRing - 1) : "memory");  // view vi has landed
             if (valid) {
@@ -864,6 +875,12 @@ __global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const _
             }
             request_view(vi + kGradRing);
         } else {
+            float4 q[4];
+            warp_load_records_finish(nr, q, s_stage[threadIdx.x >> 5]);
+            g0 = q[0];
+            g1 = q[1];
+            g2 = q[2];
+            g3 = q[3];
             request_view(vi + 1);
         }
         const int radius = valid ? V.radii[g] : 0;
@@ -1006,7 +1023,7 @@ __global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const _
     if (is_obj && a.g.gs_time_sigma) put2(reinterpret_cast<float2*>(a.g.gs_time_sigma) + j, make_float2(asig0, asig1), acc);
     if (!is_obj) {
         const float4 qraw = reinterpret_cast<const float4*>(m.rotation)[g];
-        const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+        const float qn = fmaxf(sqrtf(sumsq4_pinned(qraw.x, qraw.y, qraw.z, qraw.w)), 1e-12f);
         put4(reinterpret_cast<float4*>(a.g.rotation) + g,
              normalize4_bwd(rot_scene, qn, make_float4(adq[0], adq[1], adq[2], adq[3])), acc);
     }
@@ -1057,7 +1074,7 @@ __global__ void __launch_bounds__(TPB, MINB) rotation_backward_multi_kernel(cons
             qraw.z += r.y;
             qraw.w += r.z;
         }
-        const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+        const float qn = fmaxf(sqrtf(sumsq4_pinned(qraw.x, qraw.y, qraw.z, qraw.w)), 1e-12f);
         const float4 qhat = make_float4(qraw.x / qn, qraw.y / qn, qraw.z / qn, qraw.w / qn);
         const float4 graw = normalize4_bwd(qhat, qn, V.dq_scratch[j]);  // wxyz
         if (tb.quat.n_ctrl == 0) {
@@ -1140,7 +1157,7 @@ __global__ void __launch_bounds__(TPB, MINB) rotation_backward_views_kernel(cons
     qraw.y += r.x;
     qraw.z += r.y;
     qraw.w += r.z;
-    const float qn = fmaxf(sqrtf(qraw.x * qraw.x + qraw.y * qraw.y + qraw.z * qraw.z + qraw.w * qraw.w), 1e-12f);
+    const float qn = fmaxf(sqrtf(sumsq4_pinned(qraw.x, qraw.y, qraw.z, qraw.w)), 1e-12f);
     const float4 qhat = make_float4(qraw.x / qn, qraw.y / qn, qraw.z / qn, qraw.w / qn);
     const float4 graw = normalize4_bwd(qhat, qn, V.dq_scratch[j]);  // wxyz
     if (!grd) return;

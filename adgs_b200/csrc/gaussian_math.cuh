@@ -221,8 +221,12 @@ __device__ __forceinline__ bool splat_geometry(const float3& p, const float* sca
 __device__ __forceinline__ void sh_to_rgb(int deg, const float3& pos, const float* campos, const float* sh,
                                           float* rgb, uint32_t& clamped_bits)
 {
+    // Sums of two or more products are written with explicit intrinsics (dot3_pinned & co.): which product nvcc
+    // fuses into an FMA depends on the code around the expression, and the strict, fused and multi-view front ends
+    // must produce the same colour bits as each other and as the reference's computeColorFromSH. The patterns are
+    // the ones nvcc 12.9 emits for the reference expression (read off the SASS of the strict kernel).
     float dx = pos.x - campos[0], dy = pos.y - campos[1], dz = pos.z - campos[2];
-    const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float len = sqrtf(dot3_pinned(dx, dx, dy, dy, dz, dz));
     dx = dx / len;
     dy = dy / len;
     dz = dz / len;
@@ -235,23 +239,30 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float3& pos, const floa
         for (int c = 0; c < 3; ++c)
             res[c] = res[c] - ADGS_SH_C1 * y * sh[3 + c] + ADGS_SH_C1 * z * sh[6 + c] - ADGS_SH_C1 * x * sh[9 + c];
         if (deg > 1) {
-            const float xx = x * x, yy = y * y, zz = z * z;
-            const float xy = x * y, yz = y * z, xz = x * z;
+            const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+            const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+            const float zz2 = __fadd_rn(zz, zz);                                    // 2 zz (exact)
+            const float p20 = __fadd_rn(__fadd_rn(zz2, -xx), -yy);                  // 2zz - xx - yy
+            const float xx_yy = __fadd_rn(xx, -yy);                                 // xx - yy
 #pragma unroll
             for (int c = 0; c < 3; ++c)
                 res[c] = res[c] + ADGS_SH_C2_0 * xy * sh[12 + c] + ADGS_SH_C2_1 * yz * sh[15 + c] +
-                         ADGS_SH_C2_2 * (2.0f * zz - xx - yy) * sh[18 + c] + ADGS_SH_C2_3 * xz * sh[21 + c] +
-                         ADGS_SH_C2_4 * (xx - yy) * sh[24 + c];
+                         ADGS_SH_C2_2 * p20 * sh[18 + c] + ADGS_SH_C2_3 * xz * sh[21 + c] +
+                         ADGS_SH_C2_4 * xx_yy * sh[24 + c];
             if (deg > 2) {
+                const float p3a = __fmaf_rn(xx, 3.0f, -yy);                         // 3xx - yy
+                const float p3b = __fadd_rn(__fmaf_rn(zz, 4.0f, -xx), -yy);         // 4zz - xx - yy
+                const float p3c = __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2));  // 2zz - 3xx - 3yy
+                const float p3d = __fmaf_rn(yy, -3.0f, xx);                         // xx - 3yy
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    res[c] = res[c] + ADGS_SH_C3_0 * y * (3.0f * xx - yy) * sh[27 + c] +
+                    res[c] = res[c] + ADGS_SH_C3_0 * y * p3a * sh[27 + c] +
                              ADGS_SH_C3_1 * xy * z * sh[30 + c] +
-                             ADGS_SH_C3_2 * y * (4.0f * zz - xx - yy) * sh[33 + c] +
-                             ADGS_SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
-                             ADGS_SH_C3_4 * x * (4.0f * zz - xx - yy) * sh[39 + c] +
-                             ADGS_SH_C3_5 * z * (xx - yy) * sh[42 + c] +
-                             ADGS_SH_C3_6 * x * (xx - 3.0f * yy) * sh[45 + c];
+                             ADGS_SH_C3_2 * y * p3b * sh[33 + c] +
+                             ADGS_SH_C3_3 * z * p3c * sh[36 + c] +
+                             ADGS_SH_C3_4 * x * p3b * sh[39 + c] +
+                             ADGS_SH_C3_5 * z * xx_yy * sh[42 + c] +
+                             ADGS_SH_C3_6 * x * p3d * sh[45 + c];
             }
         }
     }

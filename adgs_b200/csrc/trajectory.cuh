@@ -15,13 +15,22 @@ struct Quat {
     float x, y, z, w;
 };
 
+// Sums of products on the forward path are written with explicit intrinsics: the single-view and the multi-view
+// kernels inline this code into different surroundings, and nvcc's choice of which product to fuse into an FMA
+// must not depend on that (the two paths are held bit-identical by tests/test_exchange_multi_gpu.py).
+__device__ __forceinline__ float sumsq4_pinned(float a, float b, float c, float d)
+{
+    return __fmaf_rn(d, d, __fmaf_rn(c, c, __fmaf_rn(b, b, __fmul_rn(a, a))));
+}
+
 __device__ __forceinline__ Quat qmul(const Quat& p, const Quat& q)
 {
     Quat r;
-    r.x = p.w * q.x + q.w * p.x + (p.y * q.z - p.z * q.y);
-    r.y = p.w * q.y + q.w * p.y + (p.z * q.x - p.x * q.z);
-    r.z = p.w * q.z + q.w * p.z + (p.x * q.y - p.y * q.x);
-    r.w = p.w * q.w - (p.x * q.x + p.y * q.y + p.z * q.z);
+    // p.w q.v + q.w p.v + p.v x q.v  |  p.w q.w - p.v . q.v
+    r.x = __fadd_rn(__fmaf_rn(q.w, p.x, __fmul_rn(p.w, q.x)), __fmaf_rn(p.y, q.z, -__fmul_rn(p.z, q.y)));
+    r.y = __fadd_rn(__fmaf_rn(q.w, p.y, __fmul_rn(p.w, q.y)), __fmaf_rn(p.z, q.x, -__fmul_rn(p.x, q.z)));
+    r.z = __fadd_rn(__fmaf_rn(q.w, p.z, __fmul_rn(p.w, q.z)), __fmaf_rn(p.x, q.y, -__fmul_rn(p.y, q.x)));
+    r.w = __fmaf_rn(p.w, q.w, -dot3_pinned(p.x, q.x, p.y, q.y, p.z, q.z));
     return r;
 }
 
@@ -126,7 +135,7 @@ __device__ __noinline__ float3 qexp_bwd(const float3& r, const Quat& e, const Qu
 __device__ __forceinline__ Quat ctrl_quat(const float4& p, float& norm)
 {
     const float w = p.x + 1.0f, x = p.y, y = p.z, z = p.w;
-    norm = fmaxf(sqrtf(w * w + x * x + y * y + z * z), 1e-12f);
+    norm = fmaxf(sqrtf(sumsq4_pinned(w, x, y, z)), 1e-12f);
     const float inv = 1.f / norm;
     return Quat{x * inv, y * inv, z * inv, w * inv};
 }

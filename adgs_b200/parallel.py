@@ -490,16 +490,21 @@ class SplatExchangeStep:
             dist.all_reduce(self.grads["background_deform"], op=dist.ReduceOp.SUM, group=self.group)
         for name in self.names:
             getattr(m, name).grad = self.grads[name]
-        if timing is not None:
-            torch.cuda.synchronize(dev)
-            marks = timing["marks"]
-            timing["calls"] = timing.get("calls", 0) + 1
-            if timing["calls"] > 10:  # skip the warm-up calls (NCCL channel set-up, allocator growth)
-                for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
-                    timing["sums"][n1] = timing["sums"].get(n1, 0.0) + e0.elapsed_time(e1)
-                timing["count"] += 1
-            timing["marks"] = []
+        self._finish_timing(dev)
         return results, stats
+
+    def _finish_timing(self, dev):
+        timing = self.__dict__.get("_timing")
+        if timing is None:
+            return
+        torch.cuda.synchronize(dev)
+        marks = timing["marks"]
+        timing["calls"] = timing.get("calls", 0) + 1
+        if timing["calls"] > 10:  # skip the warm-up calls (NCCL channel set-up, allocator growth)
+            for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+                timing["sums"][n1] = timing["sums"].get(n1, 0.0) + e0.elapsed_time(e1)
+            timing["count"] += 1
+        timing["marks"] = []
 
     def _zero_planes_async(self, dev):
         """Zero-fill of the control-point gradient planes (their B-spline windows differ between views, so the
@@ -579,6 +584,17 @@ class SplatExchangeStep:
         o = dict(dtype=torch.float32, device=dev)
         D_S = 1 if self.render_objmask else 0
         P = G * n
+        timing = self.__dict__.setdefault("_timing", None)
+        if timing is None and os.environ.get("ADGS_EXCHANGE_TIMING"):
+            timing = self.__dict__["_timing"] = {"marks": [], "sums": {}, "count": 0}
+
+        def mark(name):
+            if timing is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(torch.cuda.current_stream(dev))
+                timing["marks"].append((name, ev))
+
+        mark("start")
         for rnd in range(len(views) // G):
             batch = views[rnd * G:(rnd + 1) * G]
             keep = []
@@ -598,13 +614,16 @@ class SplatExchangeStep:
                 L.check(lib.adgs_shard_forward_multi(G, cam_arr, C.byref(cmodel), basis_arr, int(self.render_objmask),
                                                      splat_arr, state_arr, stream), "shard_forward_multi")
                 zeroed = self._zero_planes_async(dev) if first else False
+                mark("shard_forward")
                 pb.barrier(stream)          # every rank's splats of my view have landed
+                mark("barrier_1")
                 cam, flow_t = batch[r]
                 cc = cams[r]
                 H, W = int(cam.image_height), int(cam.image_width)
                 splats = L.Splats(P=P, _pad=0, record=pb.rec(r), depth_keys=pb.meta(r, 0), tiles_touched=pb.meta(r, 1),
                                   radii=pb.meta(r, 2), mean_x=pb.meta(r, 3), mean_y=pb.meta(r, 4))
                 geom, imgbuf, binning, capacity = self._bin_view(cc, splats, P, W, H, pipe, dev, stream)
+                mark("binning")
                 img = dict(color=torch.empty((3, H, W), **o), depth=torch.empty((1, H, W), **o),
                            opacity=torch.empty((1, H, W), **o), flow=torch.empty((3, H, W), **o),
                            semantic=torch.empty((D_S, H, W), **o))
@@ -618,6 +637,7 @@ class SplatExchangeStep:
                        "img_semantic": img["semantic"] if self.render_objmask else None,
                        "radii": pb.local_radii()}      # a view of the exchange buffer: valid until the next round
                 results.append(res)
+                mark("blend_forward")
                 cot = cotangent_fn((cam, flow_t), res)
                 ct = {kk: (None if cot.get(kk) is None else cot[kk].contiguous()) for kk in
                       ("color", "depth", "opacity", "flow", "semantic")}
@@ -626,7 +646,9 @@ class SplatExchangeStep:
                 L.check(lib.adgs_splats_backward(C.byref(cc), C.byref(splats), D_S, has_flow, L.ptr(binning), capacity,
                                                  L.ptr(imgbuf), L.ptr(img["opacity"]), C.byref(ig), pb.grec(r), stream),
                         "splats_backward")
+                mark("cotangents+blend_backward")
                 pb.barrier(stream)          # every rank's gradient records are complete
+                mark("barrier_2")
                 scratch = torch.empty((lib.adgs_shard_scratch_bytes(G, m.n_obj),), dtype=torch.uint8, device=dev)
                 gm = m.c_model_from(self.grads, with_time=False)
                 d2 = torch.empty((G, n, 3), **o)
@@ -639,6 +661,7 @@ class SplatExchangeStep:
                                                       grec_arr, C.byref(gm), int(not first) | (2 if zeroed else 0),
                                                       d2_arr, L.ptr(scratch), stream), "shard_backward_multi")
                 first, zeroed = False, False
+                mark("shard_backward")
                 roff = lib.adgs_shard_state_radii_offset(n)
                 for v in range(G):
                     # radii of my Gaussians in view v: the owner-side copy inside the (128-byte aligned) shard state
@@ -646,8 +669,10 @@ class SplatExchangeStep:
                     stats.append((d2[v], state[v, off:off + 4 * n].view(torch.int32)))
         if self.grads["background_deform"].numel():
             dist.all_reduce(self.grads["background_deform"], op=dist.ReduceOp.SUM, group=self.group)
+        mark("background_all_reduce")
         for name in self.names:
             getattr(m, name).grad = self.grads[name]
+        self._finish_timing(dev)
         return results, stats
 
     def timing_report(self):
