@@ -307,6 +307,7 @@ SIGNATURES = {
     "adgs_peer_open": (C.c_int, [C.c_char_p, _P(C.c_void_p)]),
     "adgs_peer_close": (C.c_int, [C.c_void_p]),
     "adgs_peer_free": (C.c_int, [C.c_void_p]),
+    "adgs_peer_sum": (C.c_int, [C.c_int32, _P(C.c_void_p), C.c_int32, C.c_void_p, C.c_void_p]),
     "adgs_peer_barrier": (C.c_int, [C.c_int32, C.c_int32, _P(C.c_void_p), C.c_uint32, C.c_void_p, C.c_void_p]),
     "adgs_adam_step": (C.c_int, [_P(AdamSegment), C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int64,
                                  C.c_void_p]),

@@ -602,7 +602,6 @@ int validate_model(const adgs_model* m, const adgs_time_basis* tb)
 // backward sums the per-view contributions in registers and writes every dense gradient once.
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxViews = 8;
-constexpr int kGradRing = 4;  // views of gradient records in flight in the multi-view backward
 
 struct ViewIO {
     adgs_time_basis tb;
@@ -781,7 +780,7 @@ __global__ void __launch_bounds__(TPB, MINB) shard_forward_multi_kernel(const __
     }
 }
 
-template <int TPB, int MINB, bool RING>
+template <int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const __grid_constant__ MultiViewArgs a)
 {
     __shared__ CamSmem cam;
@@ -820,40 +819,22 @@ __global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const _
     for (int v = 0; v < kMaxViews; ++v) ddc[v][0] = ddc[v][1] = ddc[v][2] = 0.f;
     float4 rot_scene = make_float4(1.f, 0.f, 0.f, 0.f);
 
-    // The gradient records of view v may live in ANOTHER GPU's memory (peer-memory exchange: every load is an NVLink
-    // round trip of a few microseconds), so they are requested ahead of their use:
-    //   RING  = cp.async into a ring of kGradRing views in shared memory, each thread fetching (and later reading)
-    //           only its own four quads; view v + kGradRing is requested as soon as view v has been consumed
-    //   !RING = the next view's four quads are loaded into registers before the current view's arithmetic
-    extern __shared__ float4 s_grad_ring[];  // [kGradRing][4][TPB] (RING only)
-    auto ring_slot = [&](int vi, int q) -> float4* { return s_grad_ring + ((vi % kGradRing) * 4 + q) * TPB + threadIdx.x; };
-    __shared__ float4 s_stage[TPB / 32][128];  // per warp: 32 records coming in, coalesced (warp_load_records_*)
+    // The gradient records of view v may live in ANOTHER GPU's memory (peer-memory exchange): the warp loads its 2 KB
+    // block with four fully coalesced 512-byte instructions (a lane fetching its own record would issue 16-byte
+    // loads 64 bytes apart, each its own NVLink transaction), one view AHEAD of its use so that the round trip of a
+    // few microseconds is covered by the current view's arithmetic, and transposes it through shared memory.
+    // (A cp.async ring of four views in shared memory was tried: 0.60 ms instead of 0.34 ms at 8 GPUs, removed.)
+    __shared__ float4 s_stage[TPB / 32][128];
     const int warp_g0 = g - (int)(threadIdx.x & 31);
     const size_t warp_quads = warp_g0 < N ? (size_t)(N - warp_g0) * 4 : 0;
-    float4 nr[4];  // !RING: the warp's next block, quad k of the block in lane k % 32 (coalesced), not yet transposed
+    float4 nr[4];  // the warp's next block, quad k of the block in lane k % 32, not yet transposed
     nr[0] = nr[1] = nr[2] = nr[3] = make_float4(0.f, 0.f, 0.f, 0.f);
     auto request_view = [&](int vi) {
-        if (RING) {
-            if (valid && vi < a.num_views) {
-                const float4* gr = reinterpret_cast<const float4*>(a.v[vi].grad_record) + (size_t)g * 4;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t d = (uint32_t)__cvta_generic_to_shared(ring_slot(vi, q));
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gr + q) : "memory");
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");  // one group per view, empty or not
-        } else if (vi < a.num_views) {
+        if (vi < a.num_views)
             warp_load_records_issue(reinterpret_cast<const float4*>(a.v[vi].grad_record) + (size_t)warp_g0 * 4, warp_quads,
                                     nr);
-        }
     };
-    if (RING) {
-#pragma unroll
-        for (int vi = 0; vi < kGradRing; ++vi) request_view(vi);
-    } else {
-        request_view(0);
-    }
+    request_view(0);
 
 #pragma unroll
     for (int vi = 0; vi < kMaxViews; ++vi) {
@@ -864,25 +845,10 @@ __global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const _
         load_camera(cam, V.view, V.proj, V.campos, nullptr);
         const bool flow = tb.has_flow != 0;
         float dxt[3] = {0.f, 0.f, 0.f}, dfl[3] = {0.f, 0.f, 0.f};
-        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0, g3 = g0;
-        if (RING) {
-            asm volatile("cp.async.wait_group %0;" ::"n"(kGradRing - 1) : "memory");  // view vi has landed
-            if (valid) {
-                g0 = *ring_slot(vi, 0);
-                g1 = *ring_slot(vi, 1);
-                g2 = *ring_slot(vi, 2);
-                g3 = *ring_slot(vi, 3);
-            }
-            request_view(vi + kGradRing);
-        } else {
-            float4 q[4];
-            warp_load_records_finish(nr, q, s_stage[threadIdx.x >> 5]);
-            g0 = q[0];
-            g1 = q[1];
-            g2 = q[2];
-            g3 = q[3];
-            request_view(vi + 1);
-        }
+        float4 gq[4];
+        warp_load_records_finish(nr, gq, s_stage[threadIdx.x >> 5]);
+        const float4 g0 = gq[0], g1 = gq[1], g2 = gq[2], g3 = gq[3];
+        request_view(vi + 1);
         const int radius = valid ? V.radii[g] : 0;
         if (valid) {
             if (V.dL_dmeans2D) {
@@ -1832,15 +1798,7 @@ int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cams, const 
     {
         StageScope scope(kStagePerGaussianBwd, stream);
         // sweep r1l (2 GPUs): 168 registers 0.289 ms, 128 registers 0.244 ms, 230 registers 0.366 ms
-        // ADGS_TUNE_MBWD: how the (possibly remote) gradient records are prefetched: 0 = next view into registers,
-        // 1 = cp.async ring of kGradRing views in shared memory, -1 = ring when there are more views than the ring holds
-        static const int variant = tune_variant("ADGS_TUNE_MBWD", -1);
-        const bool ring = variant == 1 || (variant == -1 && num_views > kGradRing);
-        if (ring)
-            shard_backward_multi_kernel<128, 4, true>
-                <<<(N + 127) / 128, 128, (size_t)kGradRing * 4 * 128 * sizeof(float4), stream>>>(a);
-        else
-            shard_backward_multi_kernel<128, 4, false><<<(N + 127) / 128, 128, 0, stream>>>(a);
+        shard_backward_multi_kernel<128, 4><<<(N + 127) / 128, 128, 0, stream>>>(a);
         count_launch(1);
     }
     if ((st = check_stage("shard backward (multi-view)", debug, stream))) return st;

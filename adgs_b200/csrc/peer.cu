@@ -51,6 +51,22 @@ __global__ void peer_barrier_kernel(const BarrierArgs a)
     }
 }
 
+struct SumArgs {
+    const float* src[ADGS_MAX_PEERS];
+    float* out;
+    int world, n;
+};
+
+// out[i] = sum over ranks of src[rank][i] in rank order (the same order on every rank: identical results everywhere)
+__global__ void peer_sum_kernel(const SumArgs a)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < a.world; ++p) s += a.src[p][i];
+        a.out[i] = s;
+    }
+}
+
 }  // namespace
 }  // namespace adgs
 
@@ -102,6 +118,22 @@ int adgs_peer_free(void* ptr)
     if (!ptr) return ADGS_OK;
     cudaError_t e = cudaFree(ptr);
     return e == cudaSuccess ? ADGS_OK : record_cuda_error(e, "peer_free");
+}
+
+int adgs_peer_sum(int32_t world, const float* const* partials, int32_t n, float* out, adgs_stream_t stream)
+{
+    if (world < 1 || world > ADGS_MAX_PEERS || !partials || n < 0 || (n > 0 && !out)) return ADGS_ERR_ARG;
+    if (n == 0) return ADGS_OK;
+    SumArgs a;
+    for (int p = 0; p < ADGS_MAX_PEERS; ++p) a.src[p] = p < world ? partials[p] : nullptr;
+    for (int p = 0; p < world; ++p)
+        if (!a.src[p]) return ADGS_ERR_ARG;
+    a.out = out;
+    a.world = world;
+    a.n = n;
+    count_launch(1);
+    peer_sum_kernel<<<(n + 255) / 256 > 64 ? 64 : (n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(a);
+    return check_stage("peer_sum", false, (cudaStream_t)stream);
 }
 
 int adgs_peer_barrier(int32_t world, int32_t rank, uint32_t* const* flag_arrays, uint32_t epoch, uint32_t* status,

@@ -191,7 +191,8 @@ class PeerBuffers:
         import ctypes as C
         self.L, self.lib, self.world, self.rank, self.n, self.device = L, lib, world, rank, n, device
         P = world * n
-        self.off_rec = 512
+        self.off_bg = 512                       # this rank's partial of the background-trajectory gradient (<= 3.5 KB)
+        self.off_rec = 4096
         self.off_meta = self.off_rec + P * 64
         self.off_grec = self.off_meta + 5 * P * 4
         self.bytes = self.off_grec + P * 64
@@ -222,6 +223,9 @@ class PeerBuffers:
 
     def grec(self, p, slot=0):
         return self.base[p] + self.off_grec + slot * self.n * 64
+
+    def bg(self, p):
+        return self.base[p] + self.off_bg
 
     def barrier(self, stream):
         self.epoch += 1
@@ -651,6 +655,10 @@ class SplatExchangeStep:
                 mark("barrier_2")
                 scratch = torch.empty((lib.adgs_shard_scratch_bytes(G, m.n_obj),), dtype=torch.uint8, device=dev)
                 gm = m.c_model_from(self.grads, with_time=False)
+                n_bg = self.grads["background_deform"].numel()
+                assert n_bg * 4 <= pb.off_rec - pb.off_bg
+                if n_bg:
+                    gm.background_deform = pb.bg(r)     # my partial sum goes where the peers can read it
                 d2 = torch.empty((G, n, 3), **o)
                 radii_arr = (C.c_void_p * G)()      # null: the radii copy the forward kept in the shard state
                 grec_arr = (C.c_void_p * G)(*[pb.grec(v, r) for v in range(G)])         # peer loads (cp.async ring)
@@ -667,8 +675,13 @@ class SplatExchangeStep:
                     # radii of my Gaussians in view v: the owner-side copy inside the (128-byte aligned) shard state
                     off = (-state[v].data_ptr()) % 128 + roff
                     stats.append((d2[v], state[v, off:off + 4 * n].view(torch.int32)))
-        if self.grads["background_deform"].numel():
-            dist.all_reduce(self.grads["background_deform"], op=dist.ReduceOp.SUM, group=self.group)
+        # the background trajectory is shared by every Gaussian: its gradient sums over the shards (3 x C_bg floats,
+        # summed with peer loads in rank order after a barrier: identical bits on every rank, no NCCL latency)
+        n_bg = self.grads["background_deform"].numel()
+        if n_bg:
+            pb.barrier(stream)
+            parts = (C.c_void_p * G)(*[pb.bg(p) for p in range(G)])
+            L.check(lib.adgs_peer_sum(G, parts, n_bg, self.grads["background_deform"].data_ptr(), stream), "peer_sum")
         mark("background_all_reduce")
         for name in self.names:
             getattr(m, name).grad = self.grads[name]

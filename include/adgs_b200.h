@@ -420,6 +420,10 @@ ADGS_API int adgs_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
 ADGS_API int adgs_peer_open(const unsigned char* handle64, void** ptr);
 ADGS_API int adgs_peer_close(void* ptr);
 ADGS_API int adgs_peer_free(void* ptr);
+/* out[i] = sum over ranks p < world of partials[p][i] (rank order: identical bits on every rank): the all-reduce of a
+ * SMALL vector (the 3 x C_bg background-trajectory gradient every Gaussian shares) with plain peer loads, after an
+ * adgs_peer_barrier -- a latency-bound NCCL call replaced by ~10 us of kernel. */
+ADGS_API int adgs_peer_sum(int32_t world, const float* const* partials, int32_t n, float* out, adgs_stream_t stream);
 ADGS_API int adgs_peer_barrier(int32_t world, int32_t rank, uint32_t* const* flag_arrays, uint32_t epoch,
                                uint32_t* status, adgs_stream_t stream);
 
