@@ -372,14 +372,16 @@ class GaussianModel(nn.Module):
         return bool(opt is not None and getattr(opt, "window_aware", False) and opt.window_eligible())
 
     def shard(self, rank: int, world: int):
-        """Rank `rank`'s slice of the model for the splat-exchange multi-GPU path: contiguous blocks of
-        the scene and of the object Gaussians, padded to equal sizes across ranks with fully
-        transparent Gaussians (opacity logit -1e30 => alpha = 0: they contribute nothing anywhere)."""
+        """Rank `rank`'s slice of the model for the splat-exchange multi-GPU path: every world-th scene Gaussian
+        and every world-th object Gaussian starting at `rank` (row i of a block belongs to rank i % world -- a strided
+        cut balances culled / visible and near / far Gaussians across the ranks, whatever order the arrays are in),
+        padded to equal sizes across ranks with fully transparent Gaussians (opacity logit -1e30 => alpha = 0: they
+        contribute nothing anywhere)."""
         ref = self.to_reference()
         ns, no = -(-self.n_scene // world), -(-self.n_obj // world)
 
         def cut(t, n_per, pad_value=0.0):
-            part = t[rank * n_per:(rank + 1) * n_per]
+            part = t[rank::world]
             if part.shape[0] < n_per:
                 pad = torch.full((n_per - part.shape[0],) + tuple(t.shape[1:]), pad_value, dtype=t.dtype, device=t.device)
                 part = torch.cat([part, pad], dim=0)

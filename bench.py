@@ -754,8 +754,8 @@ def run_ours(args):
                 others[name] = {"error": f"{type(exc).__name__}: {exc}"}
             torch.cuda.empty_cache()
 
-    if rank == 0 and ex is not None and ex.timing_report():
-        print("exchange phases (ms):", ex.timing_report(), file=sys.stderr)
+    if ex is not None and ex.timing_report():
+        print(f"rank {rank} exchange phases (ms):", ex.timing_report(), file=sys.stderr)
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(mpix, 2), "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,

@@ -101,8 +101,7 @@ def _worker(rank, world, port, rounds):
                     if k == "background_deform_param":
                         assert Hh.rel_err(g, w) <= 1e-5, (mode, k, Hh.rel_err(g, w))
                         continue
-                    per = ns if (k.startswith("scene_") or k == "shs_deform_param_scene") else no
-                    part = w[rank * per:(rank + 1) * per]
+                    part = w[rank::world]           # the strided cut of GaussianModel.shard
                     assert Hh.rel_err(g[:part.shape[0]], part) <= 1e-5, (mode, rep, k, Hh.rel_err(g[:part.shape[0]], part))
                     frac, worst = Hh.elementwise_err(g[:part.shape[0]], part, rtol=1e-4, atol_frac=1e-5)
                     assert frac <= 1e-4, (mode, rep, k, frac, worst)
@@ -111,12 +110,12 @@ def _worker(rank, world, port, rounds):
                 for vi in range(V):
                     d2, radii = stats[vi]
                     full_d2, full_r = want_d2[vi], want_radii[vi]
-                    sl_s = slice(rank * ns, min((rank + 1) * ns, N_s))
-                    sl_o = slice(N_s + rank * no, N_s + min((rank + 1) * no, N_o))
-                    n_s, n_o = sl_s.stop - sl_s.start, sl_o.stop - sl_o.start
-                    assert Hh.rel_err(d2[:n_s], full_d2[sl_s]) <= 1e-5 and Hh.rel_err(d2[ns:ns + n_o], full_d2[sl_o]) <= 1e-5
+                    d2_s, d2_o = full_d2[:N_s][rank::world], full_d2[N_s:][rank::world]
+                    r_s, r_o = full_r[:N_s][rank::world], full_r[N_s:][rank::world]
+                    n_s, n_o = d2_s.shape[0], d2_o.shape[0]
+                    assert Hh.rel_err(d2[:n_s], d2_s) <= 1e-5 and Hh.rel_err(d2[ns:ns + n_o], d2_o) <= 1e-5
                     if radii is not None:
-                        assert torch.equal(radii[:n_s], full_r[sl_s]) and torch.equal(radii[ns:ns + n_o], full_r[sl_o])
+                        assert torch.equal(radii[:n_s], r_s) and torch.equal(radii[ns:ns + n_o], r_o)
             if ex._peer is not None:
                 assert not ex._peer.timed_out()
             dist.barrier()

@@ -462,10 +462,13 @@ def test_model_shards_partition_the_model():
     model = GaussianModel.from_reference({f: getattr(ref, f) for f in ref.FIELDS}, order_args)
     shards = [model.shard(r, 4) for r in range(4)]
     assert all(s.n_scene == 251 and s.n_obj == 84 for s in shards)
-    xyz = torch.cat([s.xyz[:s.n_scene] for s in shards])[:1001]
+    # row i of a block lives on rank i % 4 at position i // 4
+    xyz = torch.stack([s.xyz[:s.n_scene] for s in shards], dim=1).reshape(-1, 3)[:1001]
     assert torch.equal(xyz, model.xyz[:1001])
-    oxyz = torch.cat([s.xyz[s.n_scene:] for s in shards])[:334]
+    oxyz = torch.stack([s.xyz[s.n_scene:] for s in shards], dim=1).reshape(-1, 3)[:334]
     assert torch.equal(oxyz, model.xyz[1001:])
-    assert (shards[3].opacity[shards[3].n_scene - 3:shards[3].n_scene] < -1e29).all()   # padding is transparent
-    rd = torch.cat([s.rot_deform for s in shards], dim=1)[:, :334]
+    assert (shards[3].opacity[shards[3].n_scene - 1:shards[3].n_scene] < -1e29).all()   # padding is transparent
+    assert (shards[1].opacity[shards[1].n_scene - 1:shards[1].n_scene] < -1e29).all()
+    assert (shards[0].opacity[:shards[0].n_scene] > -1e29).all()                        # 1001 = 4 * 250 + 1
+    rd = torch.stack([s.rot_deform for s in shards], dim=2).reshape(shards[0].rot_deform.shape[0], -1, 4)[:, :334]
     assert torch.equal(rd, model.rot_deform)
