@@ -28,7 +28,7 @@ struct BarrierArgs {
     uint32_t* flags[ADGS_MAX_PEERS];  // flags[p] = base of rank p's flag array ([ADGS_MAX_PEERS] words, zero-initialised)
     int world, rank;
     uint32_t epoch;
-    uint32_t* status;  // local: [0] = 1 if a peer did not arrive within the timeout
+    uint32_t* status;  // local: [0] = 1 if a peer did not arrive within the timeout (the kernel then traps)
 };
 
 // Thread p: tell rank p that `rank` has reached `epoch` (everything this rank queued before the barrier is
@@ -43,9 +43,10 @@ __global__ void peer_barrier_kernel(const BarrierArgs a)
     const long long t0 = clock64();
     // epochs only grow; a signed difference tolerates wrap-around
     while ((int32_t)(ld_acquire_sys(mine) - a.epoch) < 0) {
-        if (clock64() - t0 > 4000000000ll) {  // ~2 s at 2 GHz: a peer died; do not hang the box
-            a.status[0] = 1;
-            break;
+        if (clock64() - t0 > 40000000000ll) {  // ~20 s at 2 GHz: a peer died. Neither hang the box nor carry on
+            a.status[0] = 1;                   // with half-exchanged data: record it and fail the context loudly
+            __threadfence_system();
+            __trap();
         }
         __nanosleep(64);
     }

@@ -197,20 +197,36 @@ class PeerBuffers:
         self.off_grec = self.off_meta + 5 * P * 4
         self.bytes = self.off_grec + P * 64
         with torch.cuda.device(device):
+            # every step below is collective: a rank that cannot allocate / map still takes part, and ALL ranks then
+            # raise together (SplatExchangeStep falls back to the NCCL exchange) instead of one of them hanging the rest
             ptr = C.c_void_p()
             handle = C.create_string_buffer(64)
-            L.check(lib.adgs_peer_alloc(self.bytes, C.byref(ptr), handle), "peer_alloc")
-            self.local = int(ptr.value)
+            ok = lib.adgs_peer_alloc(self.bytes, C.byref(ptr), handle) == 0
+            self.local = int(ptr.value) if ok else 0
             handles = [None] * world
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            dist.all_gather_object(handles, bytes(handle.raw) if ok else None, group=group)
             self.base = []
-            for p in range(world):
-                if p == rank:
-                    self.base.append(self.local)
-                else:
+            ok = all(h is not None for h in handles)
+            if ok:
+                for p in range(world):
+                    if p == rank:
+                        self.base.append(self.local)
+                        continue
                     q = C.c_void_p()
-                    L.check(lib.adgs_peer_open(handles[p], C.byref(q)), "peer_open")
+                    if lib.adgs_peer_open(handles[p], C.byref(q)) != 0:
+                        ok = False
+                        break
                     self.base.append(int(q.value))
+            flag = torch.tensor([1 if ok else 0], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                for p, b in enumerate(self.base):
+                    if p != rank:
+                        lib.adgs_peer_close(b)
+                if self.local:
+                    lib.adgs_peer_free(self.local)
+                raise RuntimeError("peer memory (CUDA IPC) is not available between the ranks: "
+                                   + lib.adgs_last_cuda_error().decode())
         self.flag_arr = (C.c_void_p * world)(*self.base)        # the flag words sit at offset 0
         self.status_ptr = self.local + 256
         self.epoch = 0
@@ -580,7 +596,14 @@ class SplatExchangeStep:
         if self._peer is None or self._peer.n != n:
             if self._peer is not None:
                 self._peer.close()
-            self._peer = PeerBuffers(L, lib, self.group, G, r, n, dev)
+                self._peer = None
+            try:
+                self._peer = PeerBuffers(L, lib, self.group, G, r, n, dev)
+            except RuntimeError as exc:       # raised on every rank together
+                import warnings
+                warnings.warn(f"adgs_b200: {exc}; the splat exchange falls back to NCCL all-to-all")
+                self.exchange = "nccl"
+                return self.run(views, cotangent_fn, pipe)
         pb = self._peer
         stream = torch.cuda.current_stream(dev).cuda_stream
         results, stats = [], []

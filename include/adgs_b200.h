@@ -412,7 +412,8 @@ ADGS_API int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cam
  *                      (ADGS_MAX_PEERS words inside a peer buffer, zero at start) as mapped in this process;
  *                      `epoch` must grow by one per barrier and be the same on every rank. When the barrier
  *                      completes on a rank's stream, everything every rank queued before ITS barrier has completed
- *                      (peer stores included). status (local device word): set to 1 if a peer did not arrive in ~2 s.
+ *                      (peer stores included). status (local device word): set to 1 if a peer did not arrive within ~20 s; the
+ *                      barrier kernel then traps (CUDA error on this rank) instead of continuing with half-exchanged data.
  * ---------------------------------------------------------------------------------------- */
 #define ADGS_MAX_PEERS 8
 #define ADGS_PEER_HANDLE_BYTES 64
