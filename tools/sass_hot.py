@@ -7,7 +7,8 @@ rows = list(csv.reader(open(sys.argv[1])))
 thr = float(sys.argv[2]) if len(sys.argv) > 2 else 0.15
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 h = rows[hi]
-data = [r for r in rows[hi + 1:] if len(r) == len(h)]
+nxt = next((i for i in range(hi + 1, len(rows)) if rows[i] and rows[i][0] == "Address"), len(rows))   # first launch only
+data = [r for r in rows[hi + 1:nxt] if len(r) == len(h)]
 ia, ism, ith = h.index("Instructions Executed"), h.index("# Samples"), h.index("Avg. Threads Executed")
 num = lambda s: int(s) if s.isdigit() else 0
 tot = sum(num(r[ia]) for r in data)
