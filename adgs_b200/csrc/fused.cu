@@ -995,229 +995,6 @@ __global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const _
     }
 }
 
-// View-parallel variant of shard_backward_multi_kernel for SHARDED models (N/G Gaussians x G views: too few threads
-// for one-thread-per-Gaussian, and eight views walked serially per thread). A CTA owns 32 Gaussians; warp v does view v
-// for all of them (threadIdx.x = Gaussian, threadIdx.y = view), so the expensive per-view work (cov2D / projection /
-// SH / cov3D reverse mode, the NVLink round trip of the gradient record) runs concurrently for all views. The sum over
-// the views happens in shared memory IN VIEW ORDER (one view per phase, a barrier between phases): the same order of
-// floating-point additions as the per-thread loop and as the sequential per-view oracle. Every dense gradient element
-// is then written exactly once by the CTA.
-constexpr int kViewSdRows = 48;  // 3 x SH-deform columns the view-parallel kernel supports (more: per-thread loop kernel)
-constexpr int kViewAcc = 64;  // floats per Gaussian summed over the views: xyz 3, scaling 3, quaternion 4, opacity 1,
-                              // time sigma 2, SH 48 (+3 pad)
-template <int MINB>
-__global__ void __launch_bounds__(32 * kMaxViews, MINB) shard_backward_views_kernel(const __grid_constant__ MultiViewArgs a)
-{
-    __shared__ CamSmem s_cam[kMaxViews];
-    __shared__ float s_wshs[kMaxViews][ADGS_MAX_TERMS * 2];  // dense SH-deform weights per view and column
-    __shared__ float s_acc[kViewAcc][32];                    // sums over the views, [field][Gaussian of the CTA]
-    __shared__ float s_sd[kViewSdRows][32];                  // SH-deform gradient: sum_v ddc_v[c] w_v[col]
-    __shared__ float4 s_stage[kMaxViews][128];
-    const adgs_model& m = a.m;
-    const int N = m.N_scene + m.N_obj;
-    const int lane = threadIdx.x, vi = threadIdx.y, tid = vi * 32 + lane, nthreads = 32 * a.num_views;
-    const ViewIO& V = a.v[vi];
-    const adgs_time_basis& tb = V.tb;
-    const int Cs = a.v[0].tb.shs.n_cols;
-
-    for (int i = tid; i < kMaxViews * ADGS_MAX_TERMS * 2; i += nthreads) (&s_wshs[0][0])[i] = 0.f;
-    for (int i = tid; i < kViewAcc * 32; i += nthreads) (&s_acc[0][0])[i] = 0.f;
-    for (int i = tid; i < kViewSdRows * 32; i += nthreads) (&s_sd[0][0])[i] = 0.f;
-    // this view's camera (load_camera's layout, one warp per view)
-    if (lane < 16) {
-        s_cam[vi].view[lane] = V.view[lane];
-        s_cam[vi].proj[lane] = V.proj[lane];
-    } else if (lane < 19) {
-        s_cam[vi].campos[lane - 16] = V.campos ? V.campos[lane - 16] : 0.f;
-    }
-    __syncthreads();
-    if (lane == 0)
-        for (int t = 0; t < tb.shs.n; ++t) s_wshs[vi][tb.shs.col[t]] += tb.shs.w0[t];
-    __syncwarp();  // s_wshs[vi] is read by this warp only
-    const CamSmem& cam = s_cam[vi];
-
-    const int g0 = blockIdx.x * 32;
-    const int g = g0 + lane;
-    const bool valid = g < N;
-    const bool is_obj = valid && g >= m.N_scene;
-    const int j = g - m.N_scene;
-
-    // the warp's 32 gradient records of this view, coalesced (they may live in another GPU's memory)
-    float4 gq[4];
-    {
-        float4 nr[4];
-        warp_load_records_issue(reinterpret_cast<const float4*>(V.grad_record) + (size_t)g0 * 4,
-                                g0 < N ? (size_t)(N - g0) * 4 : 0, nr);
-        warp_load_records_finish(nr, gq, s_stage[vi]);
-    }
-    const float4 g0q = gq[0], g1 = gq[1], g2 = gq[2], g3 = gq[3];
-
-    float scale[3] = {1.f, 1.f, 1.f}, sig = 0.f;
-    float vxyz[3] = {0.f, 0.f, 0.f}, vscale[3] = {0.f, 0.f, 0.f}, vdq[4] = {0.f, 0.f, 0.f, 0.f};
-    float vop = 0.f, vsig0 = 0.f, vsig1 = 0.f;
-    float dsh[48];
-#pragma unroll
-    for (int i = 0; i < 48; ++i) dsh[i] = 0.f;
-    float dxt[3] = {0.f, 0.f, 0.f}, dfl[3] = {0.f, 0.f, 0.f};
-    float4 rot_scene = make_float4(1.f, 0.f, 0.f, 0.f);
-    const bool flow = tb.has_flow != 0;
-    if (valid) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) scale[d] = expf(m.scaling[3 * (size_t)g + d]);
-        sig = 1.0f / (1.0f + expf(-m.opacity[g]));
-        if (V.dL_dmeans2D) {
-            V.dL_dmeans2D[3 * (size_t)g + 0] = g0q.x;
-            V.dL_dmeans2D[3 * (size_t)g + 1] = g0q.y;
-            V.dL_dmeans2D[3 * (size_t)g + 2] = 0.f;
-        }
-        const bool visible = V.radii[g] > 0;
-        const float4 sv0 = V.saved[(size_t)g * 3 + 0];
-        const float4 sv1 = V.saved[(size_t)g * 3 + 1];
-        const float rot[4] = {sv1.x, sv1.y, sv1.z, sv1.w};
-        if (!is_obj) rot_scene = sv1;
-        float dscale[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
-        if (flow) {
-            dfl[0] = g2.z;
-            dfl[1] = g2.w;
-            dfl[2] = g3.x;
-        }
-        if (visible) {
-            const float3 p = make_float3(sv0.x, sv0.y, sv0.z);
-            float cv[6], dcov[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) cv[i] = V.cov3D[(size_t)g * 6 + i];
-            const float3 dm = cov2d_bwd(p, V.rp, cv, cam.view, g0q.z, g0q.w, g1.x, dcov);
-            const float3 dm2 = mean_proj_depth_bwd(p, cam.view, cam.proj, g0q.x, g0q.y, g2.y, V.rp.inv_depth);
-            const float4 sv2 = V.saved[(size_t)g * 3 + 2];
-            const float4* sh4 = reinterpret_cast<const float4*>(m.sh4);
-            float sh[48];
-#pragma unroll
-            for (int q = 0; q < 12; ++q) {
-                const float4 v = __ldg(sh4 + (size_t)q * N + g);
-                sh[4 * q + 0] = v.x;
-                sh[4 * q + 1] = v.y;
-                sh[4 * q + 2] = v.z;
-                sh[4 * q + 3] = v.w;
-            }
-            sh[0] = sv2.x;
-            sh[1] = sv2.y;
-            sh[2] = sv2.z;
-            const float dcol[3] = {g1.z, g1.w, g2.x};
-            const float3 dm3 = sh_to_rgb_bwd(V.rp.sh_degree, p, cam.campos, sh, V.clamped[g], dcol, dsh);
-            dxt[0] = dm.x + dm2.x + dm3.x;
-            dxt[1] = dm.y + dm2.y + dm3.y;
-            dxt[2] = dm.z + dm2.z + dm3.z;
-            cov3d_bwd(scale, V.rp.scale_modifier, rot, dcov, dscale, dq);
-        }
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            vxyz[d] = dxt[d] + dfl[d];
-            vscale[d] = dscale[d] * scale[d];
-        }
-        {
-            const float dop = g1.y;
-            float mask = 1.f;
-            if (is_obj && tb.use_time_mask) {
-                const float delta = tb.t - m.gs_time[j];
-                const float2 sgm = reinterpret_cast<const float2*>(m.gs_time_sigma)[j];
-                const bool neg = delta < 0.0f;
-                const float sigma = expf(neg ? sgm.x : sgm.y);
-                const float z = delta / sigma;
-                mask = expf(-0.5f * z * z);
-                const float dside = dop * sig * mask * z * z;
-                if (neg) vsig0 = dside; else vsig1 = dside;
-            }
-            vop = dop * mask * sig * (1.f - sig);
-        }
-        if (!is_obj) {
-#pragma unroll
-            for (int d = 0; d < 4; ++d) vdq[d] = dq[d];
-        } else {
-            V.dq_scratch[j] = make_float4(dq[0], dq[1], dq[2], dq[3]);
-        }
-    }
-    // background parameter of this view: warp reduction of sum dxyz_t / sum dflow
-    if (tb.background.n) {
-        float r[6] = {dxt[0], dxt[1], dxt[2], dfl[0], dfl[1], dfl[2]};
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) r[i] += __shfl_xor_sync(0xffffffffu, r[i], off);
-            if (lane == 0 && r[i] != 0.f) atomicAdd(V.bg_scratch + i, r[i]);
-        }
-    }
-
-    // ---- the views add their contributions one after the other (view order = the order of the sequential sum) ----
-    for (int v = 0; v < a.num_views; ++v) {
-        if (v == vi && valid) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                s_acc[d][lane] += vxyz[d];
-                s_acc[3 + d][lane] += vscale[d];
-            }
-#pragma unroll
-            for (int d = 0; d < 4; ++d) s_acc[6 + d][lane] += vdq[d];
-            s_acc[10][lane] += vop;
-            s_acc[11][lane] += vsig0;
-            s_acc[12][lane] += vsig1;
-#pragma unroll
-            for (int i = 0; i < 48; ++i) s_acc[13 + i][lane] += dsh[i];
-            for (int e = 0; e < 3 * Cs; ++e) {
-                const int c = e / Cs;
-                const float dc = c == 0 ? dsh[0] : (c == 1 ? dsh[1] : dsh[2]);
-                s_sd[e][lane] += dc * s_wshs[vi][e - c * Cs];
-            }
-            // windows differ between views: read-modify-write on planes zero-filled before the kernel; the views of one
-            // Gaussian take turns (this loop), so the additions do not race
-            if (is_obj && tb.xyz.n && a.g.xyz_deform) {
-                for (int t = 0; t < tb.xyz.n; ++t) {
-                    float* o = a.g.xyz_deform + ((size_t)tb.xyz.col[t] * 3) * m.N_obj + j;
-                    const float w0 = tb.xyz.w0[t], w1 = tb.xyz.w1[t];
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) o[(size_t)d * m.N_obj] += dxt[d] * w0 + dfl[d] * w1;
-                }
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- every dense gradient element once: the CTA's 32 Gaussians x fields spread over all its threads ----
-    const int acc = a.accumulate;
-    if (valid) {
-        float4* gsh4 = reinterpret_cast<float4*>(a.g.sh4);
-        for (int q = vi; q < 12; q += a.num_views)
-            put4(gsh4 + (size_t)q * N + g, make_float4(s_acc[13 + 4 * q][lane], s_acc[14 + 4 * q][lane],
-                                                      s_acc[15 + 4 * q][lane], s_acc[16 + 4 * q][lane]), acc);
-        if (a.g.shs_deform4 && Cs > 0) {
-            const int nq = (3 * Cs + 3) / 4;
-            float4* gsd = reinterpret_cast<float4*>(a.g.shs_deform4);
-            for (int q = vi; q < nq; q += a.num_views) {
-                float v[4];
-#pragma unroll
-                for (int e4 = 0; e4 < 4; ++e4) v[e4] = (4 * q + e4 < 3 * Cs) ? s_sd[4 * q + e4][lane] : 0.f;
-                put4(gsd + (size_t)q * N + g, make_float4(v[0], v[1], v[2], v[3]), acc);
-            }
-        }
-        if (vi == 0) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                put(a.g.xyz + 3 * (size_t)g + d, s_acc[d][lane], acc);
-                put(a.g.scaling + 3 * (size_t)g + d, s_acc[3 + d][lane], acc);
-            }
-            put(a.g.opacity + g, s_acc[10][lane], acc);
-            if (is_obj && a.g.gs_time_sigma)
-                put2(reinterpret_cast<float2*>(a.g.gs_time_sigma) + j, make_float2(s_acc[11][lane], s_acc[12][lane]), acc);
-            if (!is_obj) {
-                const float4 qraw = reinterpret_cast<const float4*>(m.rotation)[g];
-                const float qn = fmaxf(sqrtf(sumsq4_pinned(qraw.x, qraw.y, qraw.z, qraw.w)), 1e-12f);
-                put4(reinterpret_cast<float4*>(a.g.rotation) + g,
-                     normalize4_bwd(rot_scene, qn, make_float4(s_acc[6][lane], s_acc[7][lane], s_acc[8][lane], s_acc[9][lane])),
-                     acc);
-            }
-        }
-    }
-}
-
 // Rotation chain of the object Gaussians for every view of the batch; the control-quaternion windows
 // differ between views, so the (host zero-filled) planes are accumulated with read-modify-write.
 template <int TPB, int MINB>
@@ -2021,16 +1798,7 @@ int adgs_shard_backward_multi(int32_t num_views, const adgs_camera* cams, const 
     {
         StageScope scope(kStagePerGaussianBwd, stream);
         // sweep r1l (2 GPUs): 168 registers 0.289 ms, 128 registers 0.244 ms, 230 registers 0.366 ms
-        // ADGS_TUNE_MBWD: 0 = one thread per Gaussian walks the views (parameters read once: large shards, camera rigs on
-        // one GPU), 1 = view-parallel CTAs (32 Gaussians x views; sharded models: N/G Gaussians are too few threads),
-        // -1 = by shard size
-        static const int variant = tune_variant("ADGS_TUNE_MBWD", -1);
-        const bool by_view = 3 * bases[0].shs.n_cols <= kViewSdRows &&
-                             (variant == 1 || (variant == -1 && num_views > 1 && (long long)N * num_views <= 2000000ll));
-        if (by_view)
-            shard_backward_views_kernel<2><<<(N + 31) / 32, dim3(32, num_views), 0, stream>>>(a);
-        else
-            shard_backward_multi_kernel<128, 4><<<(N + 127) / 128, 128, 0, stream>>>(a);
+        shard_backward_multi_kernel<128, 4><<<(N + 127) / 128, 128, 0, stream>>>(a);
         count_launch(1);
     }
     if ((st = check_stage("shard backward (multi-view)", debug, stream))) return st;
