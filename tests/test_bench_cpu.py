@@ -50,5 +50,5 @@ def test_elementwise_metric_catches_what_the_max_norm_hides():
     a = torch.tensor([1.0, 1e-3, 2e-3])             # a 100 % error on a small entry
     assert abs(Hh.rel_err(a, b) - 1e-3) < 1e-9      # "1e-3 relative" in the max norm ...
     frac, worst = Hh.elementwise_err(a, b, rtol=1e-4, atol_frac=1e-6)
-    assert abs(frac - 1 / 3) < 1e-12 and worst > 1000   # ... but one element in three is off by far more than 1e-4
+    assert abs(frac - 1 / 3) < 1e-12 and worst > 500   # ... but one element in three is off by ~900x its bound
     assert Hh.elementwise_err(b, b)[0] == 0.0
