@@ -278,6 +278,8 @@ struct FusedBwdArgs {
     float* dL_dmeans2D;
     float4* dq_scratch;  // (N_obj) dL/d(normalised object quaternion)
     float* bg_scratch;   // 6 floats: sum dxyz_t, sum dflow
+    float4* dm3_scratch; // (N) dL/d(position) through the view direction of the SH colour, written by sh_backward_kernel
+                         // (null: the SH block is handled inside fused_backward_kernel)
     int accumulate;      // != 0: add into the gradient buffers (second and later views of a batch)
 };
 
@@ -308,11 +310,19 @@ __device__ __forceinline__ void put4(float4* p, float4 v, int acc)
     *p = v;
 }
 
-template <int TPB, int MINB>
+// shs_deform planes are float4 quads over the flattened (channel, column) index e = c * Cs + col; the channel e / Cs
+// of every element is tabulated once per CTA (Cs is a run-time divisor)
+constexpr int kShsDeformElems = (3 * 2 * ADGS_MAX_TERMS + 3) / 4 * 4;
+
+// SH_SPLIT: the SH colour block (192 B read + 336 B written per Gaussian, 96 live registers) is handled by
+// sh_backward_kernel, which ran before and left dL/d(position) through the view direction in dm3_scratch: without the
+// two 48-float arrays this kernel fits in fewer registers and more warps cover its HBM latency.
+template <int TPB, int MINB, bool SH_SPLIT>
 __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_constant__ FusedBwdArgs a)
 {
     __shared__ CamSmem cam;
     __shared__ float s_wshs[ADGS_MAX_TERMS * 2];  // dense SH-deform weights per column
+    __shared__ uint8_t s_chan[SH_SPLIT ? 4 : kShsDeformElems];  // channel of every flattened shs_deform element
     __shared__ float s_red[TPB / 32][6];
     const adgs_model& m = a.m;
     const adgs_time_basis& tb = a.tb;
@@ -322,6 +332,8 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
     __syncthreads();
     if (threadIdx.x == 0)
         for (int t = 0; t < tb.shs.n; ++t) s_wshs[tb.shs.col[t]] += tb.shs.w0[t];
+    if (!SH_SPLIT && Cs > 0)
+        for (int e = threadIdx.x; e < (3 * Cs + 3) / 4 * 4; e += blockDim.x) s_chan[e] = (uint8_t)(e / Cs);
     load_camera(cam, a.view, a.proj, a.campos, nullptr);
 
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -343,14 +355,23 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
         const float4 sv0 = a.saved[(size_t)g * 3 + 0];
         const float4 sv1 = a.saved[(size_t)g * 3 + 1];
         const float rot[4] = {sv1.x, sv1.y, sv1.z, sv1.w};
+        // SH_SPLIT: every load of the thread is issued here, none behind the visibility branch (one DRAM latency
+        // per thread instead of three)
+        float4 dm3_pre = make_float4(0.f, 0.f, 0.f, 0.f), qraw_pre = make_float4(0.f, 0.f, 0.f, 0.f);
+        float opacity_pre = 0.f;
+        if (SH_SPLIT) {
+            dm3_pre = a.dm3_scratch[g];
+            opacity_pre = m.opacity[g];
+            if (!is_obj) qraw_pre = reinterpret_cast<const float4*>(m.rotation)[g];
+        }
         float scale[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) scale[d] = expf(m.scaling[3 * (size_t)g + d]);
 
         float dscale[3] = {0.f, 0.f, 0.f}, dq[4] = {0.f, 0.f, 0.f, 0.f};
-        float dsh[48];
+        float dsh[SH_SPLIT ? 1 : 48];
 #pragma unroll
-        for (int i = 0; i < 48; ++i) dsh[i] = 0.f;
+        for (int i = 0; i < (SH_SPLIT ? 1 : 48); ++i) dsh[i] = 0.f;
         if (flow) {
             dfl[0] = g2.z;
             dfl[1] = g2.w;
@@ -359,6 +380,10 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
         const float3 p = make_float3(sv0.x, sv0.y, sv0.z);
         float3 dm3 = make_float3(0.f, 0.f, 0.f);
         auto sh_block = [&]() {
+            if (SH_SPLIT) {
+                dm3 = make_float3(dm3_pre.x, dm3_pre.y, dm3_pre.z);
+                return;
+            }
             const float4 sv2 = a.saved[(size_t)g * 3 + 2];
             const float4* sh4 = reinterpret_cast<const float4*>(m.sh4);
             float sh[48];
@@ -380,6 +405,7 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
             dm3 = sh_to_rgb_bwd(deg, p, cam.campos, sh, a.clamped[g], dcol, dsh);
         };
         auto sh_store = [&]() {
+            if (SH_SPLIT) return;
             float4* gsh4 = reinterpret_cast<float4*>(a.g.sh4);
 #pragma unroll
             for (int q = 0; q < 12; ++q)
@@ -396,7 +422,7 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
 #pragma unroll
                     for (int e4 = 0; e4 < 4; ++e4) {
                         const int e = 4 * q + e4;
-                        const int c = e / Cs;
+                        const int c = s_chan[e];
                         const float dc = c == 0 ? dc0 : (c == 1 ? dc1 : dc2);
                         v[e4] = (c < 3) ? dc * s_wshs[e - c * Cs] : 0.f;
                     }
@@ -406,8 +432,14 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
         };
         if (visible) {
             float cv[6], dcov[6];
+            if (SH_SPLIT) {
+                // the forward's own expression on the same inputs (pinned contraction: the stored bits), cheaper than
+                // a dependent 24-byte load
+                cov3d_from_scale_rot(scale, a.rp.scale_modifier, rot, cv);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) cv[i] = a.cov3D[(size_t)g * 6 + i];
+                for (int i = 0; i < 6; ++i) cv[i] = a.cov3D[(size_t)g * 6 + i];
+            }
             float3 dm = cov2d_bwd(p, a.rp, cv, cam.view, g0.z, g0.w, g1.x, dcov);
             const float3 dm2 = mean_proj_depth_bwd(p, cam.view, cam.proj, g0.x, g0.y, g2.y, a.rp.inv_depth);
             sh_block();
@@ -427,7 +459,7 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
         // opacity: op_act = sigmoid(o) [* mask]
         {
             const float dop = g1.y;
-            const float sig = 1.0f / (1.0f + expf(-m.opacity[g]));
+            const float sig = 1.0f / (1.0f + expf(-(SH_SPLIT ? opacity_pre : m.opacity[g])));
             float mask = 1.f;
             if (is_obj && tb.use_time_mask) {
                 const float delta = tb.t - m.gs_time[j];
@@ -447,7 +479,7 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
         }
         // rotation
         if (!is_obj) {
-            const float4 qraw = reinterpret_cast<const float4*>(m.rotation)[g];
+            const float4 qraw = SH_SPLIT ? qraw_pre : reinterpret_cast<const float4*>(m.rotation)[g];
             const float qn = fmaxf(sqrtf(sumsq4_pinned(qraw.x, qraw.y, qraw.z, qraw.w)), 1e-12f);
             put4(reinterpret_cast<float4*>(a.g.rotation) + g,
                  normalize4_bwd(make_float4(rot[0], rot[1], rot[2], rot[3]), qn, make_float4(dq[0], dq[1], dq[2], dq[3])),
@@ -483,6 +515,97 @@ __global__ void __launch_bounds__(TPB, MINB) fused_backward_kernel(const __grid_
 #pragma unroll
             for (int w = 0; w < TPB / 32; ++w) s += s_red[w][threadIdx.x];
             if (s != 0.f) atomicAdd(a.bg_scratch + threadIdx.x, s);
+        }
+    }
+}
+
+// The SH colour block of the per-Gaussian backward as its own streaming kernel (see fused_backward_kernel<SH_SPLIT>):
+// dL/d(sh4) (dense: zeros for culled Gaussians), dL/d(shs_deform4) = dL/d(DC) x the time weights, and the gradient of
+// the colour w.r.t. the position through the normalised view direction (-> dm3_scratch).
+template <int TPB, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) sh_backward_kernel(const __grid_constant__ FusedBwdArgs a)
+{
+    // weight and channel of every flattened shs_deform element (kShsDeformElems above)
+    __shared__ float s_wshs[ADGS_MAX_TERMS * 2];
+    __shared__ __align__(16) float s_w[kShsDeformElems];
+    __shared__ __align__(4) uint8_t s_c[kShsDeformElems];
+    __shared__ float s_campos[3];
+    const adgs_model& m = a.m;
+    const adgs_time_basis& tb = a.tb;
+    const int N = m.N_scene + m.N_obj;
+    const int Cs = (a.g.shs_deform4 && tb.shs.n_cols > 0) ? tb.shs.n_cols : 0;
+    const int nq = (3 * Cs + 3) / 4;
+    for (int i = threadIdx.x; i < Cs && i < ADGS_MAX_TERMS * 2; i += blockDim.x) s_wshs[i] = 0.f;
+    if (threadIdx.x < 3) s_campos[threadIdx.x] = a.campos[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int t = 0; t < tb.shs.n; ++t) s_wshs[tb.shs.col[t]] += tb.shs.w0[t];
+    __syncthreads();
+    for (int e = threadIdx.x; e < 4 * nq; e += blockDim.x) {
+        const int c = e / Cs;
+        s_c[e] = (uint8_t)c;
+        s_w[e] = (c < 3) ? s_wshs[e - c * Cs] : 0.f;
+    }
+    __syncthreads();
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= N) return;
+
+    // all the unconditional loads first, the 192-byte coefficient block only for Gaussians on screen
+    const float4* gr = reinterpret_cast<const float4*>(a.grad_record) + (size_t)g * 4;
+    const bool visible = a.radii[g] > 0;
+    const float4 g1 = gr[1], g2 = gr[2];
+    const float4 sv0 = a.saved[(size_t)g * 3 + 0];
+    const float4 sv2 = a.saved[(size_t)g * 3 + 2];
+    const uint32_t clamped = a.clamped[g];
+    float basis[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) basis[k] = 0.f;
+    float gm[3] = {0.f, 0.f, 0.f};
+    float3 dm3 = make_float3(0.f, 0.f, 0.f);
+    if (visible) {
+        const float4* sh4 = reinterpret_cast<const float4*>(m.sh4);
+        float sh[48];
+        const int deg = a.rp.sh_degree;
+        const int chunks = sh_chunks_for_degree(deg);
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < chunks) v = __ldg(sh4 + (size_t)q * N + g);
+            sh[4 * q + 0] = v.x;
+            sh[4 * q + 1] = v.y;
+            sh[4 * q + 2] = v.z;
+            sh[4 * q + 3] = v.w;
+        }
+        sh[0] = sv2.x;
+        sh[1] = sv2.y;
+        sh[2] = sv2.z;
+        const float dcol[3] = {g1.z, g1.w, g2.x};
+        dm3 = sh_to_rgb_bwd<false, true>(deg, make_float3(sv0.x, sv0.y, sv0.z), s_campos, sh, clamped, dcol, basis);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gm[c] = dcol[c] * ((clamped >> c) & 1u ? 0.f : 1.f);
+    }
+    a.dm3_scratch[g] = make_float4(dm3.x, dm3.y, dm3.z, 0.f);
+    // dL/dsh[3k + c] = basis[k] * gm[c]
+    float4* gsh4 = reinterpret_cast<float4*>(a.g.sh4);
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+        float v[4];
+#pragma unroll
+        for (int e4 = 0; e4 < 4; ++e4) v[e4] = basis[(4 * q + e4) / 3] * gm[(4 * q + e4) % 3];
+        put4(gsh4 + (size_t)q * N + g, make_float4(v[0], v[1], v[2], v[3]), a.accumulate);
+    }
+    if (nq > 0) {
+        float4* gsd = reinterpret_cast<float4*>(a.g.shs_deform4);
+        const float dc0 = basis[0] * gm[0], dc1 = basis[0] * gm[1], dc2 = basis[0] * gm[2];
+        auto term = [&](uint32_t c, float w) {
+            const float dc = c == 0 ? dc0 : (c == 1 ? dc1 : dc2);
+            return (c < 3) ? dc * w : 0.f;
+        };
+        for (int q = 0; q < nq; ++q) {
+            const float4 w = reinterpret_cast<const float4*>(s_w)[q];
+            const uchar4 c = reinterpret_cast<const uchar4*>(s_c)[q];
+            put4(gsd + (size_t)q * N + g, make_float4(term(c.x, w.x), term(c.y, w.y), term(c.z, w.z), term(c.w, w.w)),
+                 a.accumulate);
         }
     }
 }
@@ -786,10 +909,13 @@ __global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const _
     __shared__ CamSmem cam;
     __shared__ float s_wshs[kMaxViews][ADGS_MAX_TERMS * 2];  // dense SH-deform weights per view and column
     __shared__ float s_red[8][6];
+    __shared__ uint8_t s_chan[kShsDeformElems];
     const adgs_model& m = a.m;
     const int N = m.N_scene + m.N_obj;
     const int Cs = a.v[0].tb.shs.n_cols;
     for (int i = threadIdx.x; i < kMaxViews * ADGS_MAX_TERMS * 2; i += blockDim.x) (&s_wshs[0][0])[i] = 0.f;
+    if (Cs > 0)
+        for (int e = threadIdx.x; e < (3 * Cs + 3) / 4 * 4; e += blockDim.x) s_chan[e] = (uint8_t)(e / Cs);
     __syncthreads();
     if (threadIdx.x < (unsigned)a.num_views) {
         const adgs_lin_basis& b = a.v[threadIdx.x].tb.shs;
@@ -973,7 +1099,7 @@ __global__ void __launch_bounds__(TPB, MINB) shard_backward_multi_kernel(const _
 #pragma unroll
             for (int e4 = 0; e4 < 4; ++e4) {
                 const int e = 4 * q + e4;
-                const int c = e / Cs;
+                const int c = s_chan[e];
                 float sum = 0.f;
                 if (c < 3) {
 #pragma unroll
@@ -1187,8 +1313,23 @@ void launch_fused_backward(const FusedBwdArgs& a, int N, cudaStream_t stream)
     // sweep r1w: the run-time index dsh[e / Cs] had put the 48-float SH gradient array into local memory; with the DC
     // gradient in scalars 0.221 -> 0.201 ms. Consuming / storing the SH block before the covariance chain: no
     // change (0.200); 5 CTAs/SM at 96 registers 0.219-0.227 ms
-    case 1: fused_backward_kernel<256, 2><<<(N + 255) / 256, 256, 0, stream>>>(a); break;
-    default: fused_backward_kernel<128, 4><<<(N + 127) / 128, 128, 0, stream>>>(a); break;
+    case 1: fused_backward_kernel<256, 2, false><<<(N + 255) / 256, 256, 0, stream>>>(a); break;
+    case 2: fused_backward_kernel<128, 4, false><<<(N + 127) / 128, 128, 0, stream>>>(a); break;
+    default:
+        if (a.dm3_scratch) {
+            // SH block as its own streaming kernel (96 registers, no spill); the rest then fits 80 registers
+            // (6 CTAs/SM instead of 4). sweep r2sh2, per_gaussian_backward stage: unsplit 0.187 ms, split 0.179;
+            // variants 3..5: 80 registers for the SH kernel (0.182) / 96 for the main kernel (0.182) / both (0.186)
+            const int grid = (N + 127) / 128;
+            if (v == 3 || v == 5) sh_backward_kernel<128, 6><<<grid, 128, 0, stream>>>(a);
+            else sh_backward_kernel<128, 5><<<grid, 128, 0, stream>>>(a);
+            if (v == 4 || v == 5) fused_backward_kernel<128, 5, true><<<grid, 128, 0, stream>>>(a);
+            else fused_backward_kernel<128, 6, true><<<grid, 128, 0, stream>>>(a);
+            count_launch(1);
+        } else {
+            fused_backward_kernel<128, 4, false><<<(N + 127) / 128, 128, 0, stream>>>(a);
+        }
+        break;
     }
     count_launch(1);
 }
@@ -1340,7 +1481,8 @@ SideStream& side_stream()
 int run_per_gaussian_backward(const adgs_camera* cam, const adgs_model* model, const adgs_time_basis* basis,
                               const int32_t* radii, const float* cov3D, const uint8_t* clamped, const float4* saved,
                               const float* grad_record, const adgs_model* grads, int accumulate, float* dL_dmeans2D,
-                              float4* dq_scratch, float* bg_scratch, cudaStream_t stream, bool fills_done = false)
+                              float4* dq_scratch, float* bg_scratch, cudaStream_t stream, bool fills_done = false,
+                              float4* dm3_scratch = nullptr)
 {
     const bool debug = cam->debug != 0;
     const int N = model->N_scene + model->N_obj;
@@ -1368,6 +1510,7 @@ int run_per_gaussian_backward(const adgs_camera* cam, const adgs_model* model, c
     a.dL_dmeans2D = dL_dmeans2D;
     a.dq_scratch = dq_scratch;
     a.bg_scratch = bg_scratch;
+    a.dm3_scratch = dm3_scratch;
     a.accumulate = accumulate;
     {
         StageScope sc(kStagePerGaussianBwd, stream);
@@ -1429,7 +1572,8 @@ size_t adgs_render_saved_bytes(int32_t N)
 
 size_t adgs_render_scratch_bytes(int32_t N, int32_t N_obj)
 {
-    return (size_t)(N > 0 ? N : 0) * ADGS_GRAD_FLOATS * sizeof(float) + (size_t)(N_obj > 0 ? N_obj : 1) * 16 + 1024;
+    // gradient records (N x 64 B) + dq (N_obj x 16 B) + background sums + dm3 (N x 16 B, SH kernel -> main kernel)
+    return (size_t)(N > 0 ? N : 0) * (ADGS_GRAD_FLOATS * sizeof(float) + 16) + (size_t)(N_obj > 0 ? N_obj : 1) * 16 + 1280;
 }
 
 static int check_render_args(const adgs_camera* cam)
@@ -1501,6 +1645,8 @@ int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const 
     carve(sc, grad_record, (size_t)N * ADGS_GRAD_FLOATS);
     carve(sc, dq_scratch, (size_t)(model->N_obj > 0 ? model->N_obj : 1));
     carve(sc, bg_scratch, 32);
+    float4* dm3_scratch = nullptr;
+    carve(sc, dm3_scratch, (size_t)N);
     float4* saved4 = nullptr;
     carve(svc, saved4, (size_t)N * 3);
     // The zero-fill of the inactive control-point planes (~260 MB at 250 k object Gaussians) is pure HBM write
@@ -1527,7 +1673,7 @@ int adgs_render_backward(const adgs_camera* cam, const adgs_model* model, const 
     if (side_lock.owns_lock()) side_lock.unlock();
     if (st) return st;
     return run_per_gaussian_backward(cam, model, basis, radii, gs.cov3D, gs.clamped, saved4, grad_record, grads, 0,
-                                     dL_dmeans2D, dq_scratch, bg_scratch, stream, fills_done);
+                                     dL_dmeans2D, dq_scratch, bg_scratch, stream, fills_done, dm3_scratch);
 }
 
 /* ---- splat exchange: Gaussian-sharded front end / back end, view-sharded blend ------------------------ */

@@ -304,7 +304,9 @@ __device__ __forceinline__ void sh_put(float* dsh, int i, float v)
 }
 
 // ACCUM = false: dsh is overwritten (zeros above the active degree); ACCUM = true: dsh += (multi-view sums).
-template <bool ACCUM = false>
+// BASIS = true: dsh receives the 16 basis values instead (zeros above the active degree) and the caller forms
+// dL/dsh[3k + c] = dsh[k] * g[c] (g = clamp-masked dL_dcolor) when it stores, keeping 16 registers live instead of 48.
+template <bool ACCUM = false, bool BASIS = false>
 __device__ __forceinline__ float3 sh_to_rgb_bwd(int deg, const float3& pos, const float* campos, const float* sh,
                                                 uint32_t clamped_bits, const float* dL_dcolor, float* dsh)
 {
@@ -319,18 +321,26 @@ __device__ __forceinline__ float3 sh_to_rgb_bwd(int deg, const float3& pos, cons
     float dx[3] = {0.f, 0.f, 0.f}, dy[3] = {0.f, 0.f, 0.f}, dz[3] = {0.f, 0.f, 0.f};
     if (!ACCUM) {
 #pragma unroll
-        for (int i = 0; i < 48; ++i) dsh[i] = 0.f;
+        for (int i = 0; i < (BASIS ? 16 : 48); ++i) dsh[i] = 0.f;
     }
+    // coefficient k, channel c, basis value bk
+    auto emit = [&](int k, int c, float bk) {
+        if (BASIS) {
+            if (c == 0) dsh[k] = bk;
+        } else {
+            sh_put<ACCUM>(dsh, 3 * k + c, bk * g[c]);
+        }
+    };
 
 #pragma unroll
-    for (int c = 0; c < 3; ++c) sh_put<ACCUM>(dsh, c, ADGS_SH_C0 * g[c]);
+    for (int c = 0; c < 3; ++c) emit(0, c, ADGS_SH_C0);
     if (deg > 0) {
         const float b1 = -ADGS_SH_C1 * y, b2 = ADGS_SH_C1 * z, b3 = -ADGS_SH_C1 * x;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            sh_put<ACCUM>(dsh, 3 + c, b1 * g[c]);
-            sh_put<ACCUM>(dsh, 6 + c, b2 * g[c]);
-            sh_put<ACCUM>(dsh, 9 + c, b3 * g[c]);
+            emit(1, c, b1);
+            emit(2, c, b2);
+            emit(3, c, b3);
             dx[c] = -ADGS_SH_C1 * sh[9 + c];
             dy[c] = -ADGS_SH_C1 * sh[3 + c];
             dz[c] = ADGS_SH_C1 * sh[6 + c];
@@ -342,11 +352,11 @@ __device__ __forceinline__ float3 sh_to_rgb_bwd(int deg, const float3& pos, cons
                         b7 = ADGS_SH_C2_3 * xz, b8 = ADGS_SH_C2_4 * (xx - yy);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                sh_put<ACCUM>(dsh, 12 + c, b4 * g[c]);
-                sh_put<ACCUM>(dsh, 15 + c, b5 * g[c]);
-                sh_put<ACCUM>(dsh, 18 + c, b6 * g[c]);
-                sh_put<ACCUM>(dsh, 21 + c, b7 * g[c]);
-                sh_put<ACCUM>(dsh, 24 + c, b8 * g[c]);
+                emit(4, c, b4);
+                emit(5, c, b5);
+                emit(6, c, b6);
+                emit(7, c, b7);
+                emit(8, c, b8);
                 dx[c] += ADGS_SH_C2_0 * y * sh[12 + c] + ADGS_SH_C2_2 * 2.f * -x * sh[18 + c] +
                          ADGS_SH_C2_3 * z * sh[21 + c] + ADGS_SH_C2_4 * 2.f * x * sh[24 + c];
                 dy[c] += ADGS_SH_C2_0 * x * sh[12 + c] + ADGS_SH_C2_1 * z * sh[15 + c] +
@@ -362,13 +372,13 @@ __device__ __forceinline__ float3 sh_to_rgb_bwd(int deg, const float3& pos, cons
                             b15 = ADGS_SH_C3_6 * x * (xx - 3.f * yy);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    sh_put<ACCUM>(dsh, 27 + c, b9 * g[c]);
-                    sh_put<ACCUM>(dsh, 30 + c, b10 * g[c]);
-                    sh_put<ACCUM>(dsh, 33 + c, b11 * g[c]);
-                    sh_put<ACCUM>(dsh, 36 + c, b12 * g[c]);
-                    sh_put<ACCUM>(dsh, 39 + c, b13 * g[c]);
-                    sh_put<ACCUM>(dsh, 42 + c, b14 * g[c]);
-                    sh_put<ACCUM>(dsh, 45 + c, b15 * g[c]);
+                    emit(9, c, b9);
+                    emit(10, c, b10);
+                    emit(11, c, b11);
+                    emit(12, c, b12);
+                    emit(13, c, b13);
+                    emit(14, c, b14);
+                    emit(15, c, b15);
                     dx[c] += (ADGS_SH_C3_0 * sh[27 + c] * 3.f * 2.f * xy + ADGS_SH_C3_1 * sh[30 + c] * yz +
                               ADGS_SH_C3_2 * sh[33 + c] * -2.f * xy + ADGS_SH_C3_3 * sh[36 + c] * -3.f * 2.f * xz +
                               ADGS_SH_C3_4 * sh[39 + c] * (-3.f * xx + 4.f * zz - yy) +
