@@ -294,6 +294,37 @@ def test_fused_render_matches_reference_pipeline_at_full_size(name):
         assert frac <= 1e-2, (f, frac)
 
 
+def test_split_per_gaussian_backward_matches_one_kernel_form(tmp_path):
+    """adgs_render_backward runs the per-Gaussian backward as two kernels (SH colour block, then the rest); the shard
+    / multi-view entry points and ADGS_TUNE_PGB=2 keep the one-kernel form. Same scene, same cotangents, one process
+    per variant (the knob is read once per process): the two forms differ only by floating-point contraction and the
+    unordered REDs of the blend backward."""
+    import os
+    import subprocess
+    import sys
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pgb_variant_grads.py")
+    outs = {}
+    for v in ("0", "2"):
+        out = str(tmp_path / f"grads_{v}.pt")
+        env = dict(os.environ, ADGS_TUNE_PGB=v)
+        r = subprocess.run([sys.executable, script, out], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[v] = torch.load(out, weights_only=True)
+    assert outs["0"].keys() == outs["2"].keys()
+    checked = 0
+    for k, a in outs["0"].items():
+        b = outs["2"][k]
+        assert a.shape == b.shape, k
+        if not b.numel() or b.abs().max().item() == 0.0:
+            assert not a.numel() or a.abs().max().item() == 0.0, k
+            continue
+        frac, worst = Hh.elementwise_err(a, b, rtol=1e-4, atol_frac=1e-5)
+        assert frac <= 1e-4, (k, frac, worst)
+        assert Hh.rel_err(a, b) <= 5e-5, (k, Hh.rel_err(a, b))
+        checked += 1
+    assert checked >= 10
+
+
 def test_sync_free_path_equals_sync_path():
     order_args, ref, c = _scene(4000, 1000, "kitti75")
     model = GaussianModel.from_reference({f: getattr(ref, f) for f in ref.FIELDS}, order_args)
