@@ -288,6 +288,10 @@ def run_ours(args):
     rig = "rig_yaw" in wl
     vpr = len(wl["rig_yaw"]) if rig else 1          # views per rank and step
     px = vpr * px
+    if rig and world * vpr > 8:
+        # one exchange round blends world x views-per-rank views (ADGS_MAX_VIEWS = 8 per round)
+        raise SystemExit(f"workload {args.workload}: {vpr} views per rank x {world} ranks exceeds the 8 views of one "
+                         f"exchange round; run it on at most {8 // vpr} GPU(s)")
     exchange = (world > 1 and args.parallel == "exchange") or rig
     mv = MultiViewStep(model) if (world > 1 and not exchange) else None
     ex = None
