@@ -22,6 +22,7 @@ method names.
 """
 import ctypes as C
 import math
+import time
 
 import numpy as np
 import torch
@@ -184,6 +185,10 @@ class GaussianModel(nn.Module):
         self.n_scene = 0
         self.n_obj = 0
         self._binning_capacity = 0   # running bound on num_rendered for the sync-free path
+        # sync-free forwards whose counters the next forward does not wait for. 0: the host trails the device by less
+        # than one step; 1-2 made no difference to the end-to-end step time at 1 M Gaussians (the host needs 0.87 ms
+        # to queue a 1.41 ms step: profiles/r2_sf_sync_free_depth.txt), so the conservative value stays
+        self.sync_free_outstanding = 0
         self._pending = None         # (pinned counters, event) of the last sync-free forward
 
     # ---- construction ------------------------------------------------------------------------
@@ -466,19 +471,24 @@ class GaussianModel(nn.Module):
     def _defer_counter_check(self, counters, event, capacity):
         self.__dict__.setdefault("_counter_checks", []).append((counters, event, int(capacity)))
 
-    def _resolve_counter_checks(self, block: bool):
+    def _resolve_counter_checks(self, block: bool, outstanding: int = 0):
         """Look at the {num_rendered, overflow} words of earlier sync-free forwards: grow the binning arena,
         and report a dropped iteration (the device already zeroed its gradients). block=False only takes the
-        ones whose copy has landed."""
+        ones whose copy has landed; block=True waits for all but the newest `outstanding` ones (the host may then
+        run that many forwards ahead of the device, and an overflow is acted on that many iterations later)."""
         checks = self.__dict__.get("_counter_checks")
         if not checks:
             return
         rest = []
-        for counters, event, capacity in checks:
-            if not block and not event.query():
+        for i, (counters, event, capacity) in enumerate(checks):
+            must = block and i < len(checks) - outstanding
+            if not must and not event.query():
                 rest.append((counters, event, capacity))
                 continue
-            event.synchronize()
+            if not event.query():
+                w0 = time.perf_counter()
+                event.synchronize()
+                self.__dict__["_host_wait_s"] = self.__dict__.get("_host_wait_s", 0.0) + time.perf_counter() - w0
             R, ovf = int(counters[0]), bool(counters[1])
             self._note_num_rendered(R)
             if ovf or R > capacity:

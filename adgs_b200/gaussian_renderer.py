@@ -38,7 +38,9 @@ class _FusedRender(torch.autograd.Function):
                 materialize):
         lib = L.load()
         dev = xyz.device
-        model._resolve_counter_checks(block=True)   # arena size for this forward (previous step's counters)
+        # arena size for this forward from the counters of earlier steps; the newest `sync_free_outstanding` forwards
+        # may still be in flight (the host then queues the next step while the device finishes this one)
+        model._resolve_counter_checks(block=True, outstanding=int(getattr(model, "sync_free_outstanding", 0)))
         N, H, W = model.get_pts_num, int(settings.image_height), int(settings.image_width)
         o = dict(dtype=torch.float32, device=dev)
         color = torch.empty((3, H, W), **o)

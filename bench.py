@@ -274,6 +274,8 @@ def run_ours(args):
     lib = L.load()
     wl = WORKLOADS[args.workload]
     model, n_scene, n_obj = build_ours(wl, device)
+    if args.sync_free_outstanding is not None:
+        model.sync_free_outstanding = args.sync_free_outstanding
     cam, t, flow_t = view_for_rank(wl, rank, device)
     cot = make_cotangents(wl, device)
     pipe = SimpleNamespace(inv_depth=True, debug=False, sync_free=True)
@@ -453,6 +455,77 @@ def run_ours(args):
 
     copy_stream = torch.cuda.Stream(device=device)
     readback_stream = torch.cuda.Stream(device=device)
+    static_flat = host_cot.to(device) if args.e2e_ablate == "cot" else None
+    # the host-to-device rate of this box for exactly this transfer, alone (into one preallocated buffer, so that no
+    # allocation sits between the copies): h2d_bytes / rate is a floor of the e2e step whatever the kernels do -- the
+    # copy of step i+1 runs under step i, but one copy per step has to fit into a step
+    h2d_ms = None
+    try:
+        probe_dst = torch.empty(host_cot.shape, dtype=host_cot.dtype, device=device)
+        with torch.cuda.stream(copy_stream):
+            for _ in range(2):
+                probe_dst.copy_(host_cot, non_blocking=True)
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(copy_stream)
+            for _ in range(8):
+                probe_dst.copy_(host_cot, non_blocking=True)
+            c1.record(copy_stream)
+        c1.synchronize()
+        h2d_ms = c0.elapsed_time(c1) / 8
+        del probe_dst
+    except Exception as exc:   # the probe must never take the bench line down with it
+        sys.stderr.write(f"h2d probe failed: {exc}\n")
+
+    # Device-side staging of the per-step inputs: a ring of preallocated buffers, refilled every step from pinned
+    # memory on the copy stream. (A fresh device tensor per step -- `host_cot.to(device)` -- works too, but its block
+    # comes from the caching allocator's copy-stream pool, which grows by one cudaMalloc whenever the host gets one
+    # more step ahead than it had been before; a cudaMalloc costs ~14 ms on these boxes, i.e. +0.14 ms/step over a
+    # 100-step run for every one that lands inside it: profiles/r2_ab_e2e_ablation.txt. --e2e-staging alloc keeps
+    # that behaviour for comparison.) A slot is refilled only after the kernels that read it have finished: the copy
+    # stream waits for the event its last reader recorded, the host never does.
+    ring_n = 4
+    use_ring = args.e2e_staging == "ring"
+    cot_ring = [torch.empty(host_cot.shape, dtype=torch.float32, device=device) for _ in range(ring_n)] if use_ring else []
+    cam_ring = [torch.empty(host_cam.shape, dtype=torch.float32, device=device) for _ in range(ring_n)] if use_ring else []
+    slot_free = [None] * ring_n
+    staged = [0]
+
+    def stage_inputs():
+        """-> (slot, camera on the device, its event, cotangents on the device, their event); both copies go through
+        the copy stream, camera first: a tiny camera copy issued on the compute stream would queue behind the
+        16.7 MB transfer on the host-to-device copy engine and stall the forward."""
+        k = staged[0] % ring_n
+        staged[0] += 1
+        with torch.cuda.stream(copy_stream):
+            if use_ring:
+                if slot_free[k] is not None:
+                    copy_stream.wait_event(slot_free[k])
+                dcam = cam_ring[k]
+                dcam.copy_(host_cam, non_blocking=True)
+            else:
+                dcam = host_cam.to(device, non_blocking=True)
+            cam_ready = torch.cuda.Event()
+            cam_ready.record(copy_stream)
+            if args.e2e_ablate == "cot":
+                flat = static_flat
+            elif use_ring:
+                flat = cot_ring[k]
+                flat.copy_(host_cot, non_blocking=True)
+            else:
+                flat = host_cot.to(device, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        return k, dcam, cam_ready, flat, ready
+
+    def use_on_compute_stream(t):
+        if not use_ring:        # per-step tensors: tell the allocator that the compute stream reads them
+            t.record_stream(torch.cuda.current_stream(device))
+
+    def release_inputs(k):
+        if use_ring:            # everything queued on the compute stream so far may read slot k
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(device))
+            slot_free[k] = ev
 
     # device -> host read of the step's metric: an asynchronous copy into pinned memory that the host
     # consumes two steps later (after the next two steps have been queued), the way a training loop logs its
@@ -462,9 +535,13 @@ def run_ours(args):
     metric_pending = []
     metric_log = []
 
+    host_wait = [0.0]   # seconds the host spent waiting for the GPU (everything else in the loop is enqueue work)
+
     def consume_metric():
         buf, ev = metric_pending.pop(0)
+        w0 = time.perf_counter()
         ev.synchronize()
+        host_wait[0] += time.perf_counter() - w0
         metric_log.append(float(buf[0].item()))
 
     def read_metric(value_on_device):
@@ -492,15 +569,9 @@ def run_ours(args):
             consume_metric()
 
     def e2e_step_exchange():
-        with torch.cuda.stream(copy_stream):
-            dcam = host_cam.to(device, non_blocking=True)
-            cam_ready = torch.cuda.Event()
-            cam_ready.record(copy_stream)
-            flat = host_cot.to(device, non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(copy_stream)
+        slot, dcam, cam_ready, flat, ready = stage_inputs()
         torch.cuda.current_stream(device).wait_event(cam_ready)
-        dcam.record_stream(torch.cuda.current_stream(device))
+        use_on_compute_stream(dcam)
         views_ = list(all_views)
         views_[rank * vpr] = (all_views[rank * vpr][0]._replace(world_view_transform=dcam[0:16].view(4, 4),
                                                                 full_proj_transform=dcam[16:32].view(4, 4),
@@ -509,31 +580,26 @@ def run_ours(args):
 
         def cots(v, r):
             torch.cuda.current_stream(device).wait_event(ready)
-            flat.record_stream(torch.cuda.current_stream(device))
+            use_on_compute_stream(flat)
             box["res"] = r
             return split_cot(flat)
 
         ex.run(views_, cots, pipe, views_per_rank=vpr)
+        release_inputs(slot)
         read_metric(box["res"]["img_opacity"].mean())
 
     def e2e_step():
         if ex is not None:
             return e2e_step_exchange()
-        # host -> device: camera matrices first (needed by the forward), cotangent planes on a copy
-        # stream so that the PCIe transfer overlaps the forward; the backward waits for them.
-        # Both copies go through the copy stream, camera first: a tiny camera copy issued on the compute stream
-        # would queue behind the 16.7 MB transfer on the host-to-device copy engine and stall the forward.
-        with torch.cuda.stream(copy_stream):
-            dcam = host_cam.to(device, non_blocking=True)
-            cam_ready = torch.cuda.Event()
-            cam_ready.record(copy_stream)
-            flat = host_cot.to(device, non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(copy_stream)
+        # host -> device: camera matrices first (needed by the forward), cotangent planes behind them on the copy
+        # stream so that the PCIe transfer overlaps the forward; the backward waits for them (stage_inputs).
+        ablate = args.e2e_ablate      # diagnosis only (the reported e2e runs with "none")
+        slot, dcam, cam_ready, flat, ready = stage_inputs()
         torch.cuda.current_stream(device).wait_event(cam_ready)
-        dcam.record_stream(torch.cuda.current_stream(device))
-        vc = cam._replace(world_view_transform=dcam[0:16].view(4, 4), full_proj_transform=dcam[16:32].view(4, 4),
-                          camera_center=dcam[32:35])
+        use_on_compute_stream(dcam)
+        vc = cam if ablate == "cam" else cam._replace(world_view_transform=dcam[0:16].view(4, 4),
+                                                      full_proj_transform=dcam[16:32].view(4, 4),
+                                                      camera_center=dcam[32:35])
         c = split_cot(flat)
         for p in params:
             p.grad = None
@@ -541,26 +607,36 @@ def run_ours(args):
         try:
             res = render(vc, model, None, pipe, flow_pkg=flow_pkg, render_objmask=True)
             torch.cuda.current_stream(device).wait_event(ready)
-            flat.record_stream(torch.cuda.current_stream(device))
+            if flat is not static_flat:
+                use_on_compute_stream(flat)
             outs, cots = outputs_and_cotangents(res, c)
             torch.autograd.backward(outs, cots)
         finally:
             model._grad_sink = None
+        release_inputs(slot)
         if mv is not None:
             mv.bucket.all_reduce()
-        read_metric(res["img_opacity"].mean())   # device -> host read of a metric
+        if ablate == "metric":
+            metric_log.append(0.0)
+        else:
+            read_metric(res["img_opacity"].mean())   # device -> host read of a metric
 
-    for _ in range(3):
+    e2e_warm = max(3, args.warmup)
+    for _ in range(e2e_warm):
         e2e_step()
     drain_metrics()
     barrier()
+    host_wait[0] = -model.__dict__.get("_host_wait_s", 0.0)   # + the waits inside render() (binning counters)
+    h0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         e2e_step()
     drain_metrics()
     e1.record()
+    host_wait[0] += model.__dict__.get("_host_wait_s", 0.0)
+    host_ms = (time.perf_counter() - h0 - host_wait[0]) * 1e3 / args.steps
     barrier()
-    assert len(metric_log) == args.steps + 3 and all(math.isfinite(v) for v in metric_log)
+    assert len(metric_log) == args.steps + e2e_warm and all(math.isfinite(v) for v in metric_log)
     ms_e2e = e0.elapsed_time(e1) / args.steps
     if world > 1:
         tt = torch.tensor([ms_e2e], device=device)
@@ -568,6 +644,16 @@ def run_ours(args):
         ms_e2e = float(tt.item())
     e2e = {"value": round(world * px / (ms_e2e * 1e-3) / 1e6, 2), "unit": "Mpix/s", "ms_per_step": round(ms_e2e, 4),
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           # python + ctypes + launch time per step with the waits on the GPU taken out: when it approaches
+           # ms_per_step the loop is bound by the host, not by the device
+           "host_enqueue_ms_per_step": round(host_ms, 4),
+           "staging": ("ring of 4 preallocated device buffers refilled from pinned memory every step" if use_ring
+                       else "fresh device tensor per step"),
+           "h2d_alone": None if not h2d_ms else {
+               "ms_per_step": round(h2d_ms, 4), "GBps": round(host_cot.numel() * 4 / (h2d_ms * 1e-3) / 1e9, 2),
+               "note": "this step's pinned-memory transfer timed on its own (idle GPU): the PCIe floor of the e2e "
+                       "step on this box"},
+           **({"INVALID_ablated": args.e2e_ablate} if args.e2e_ablate != "none" else {}),
            "readback": "blocking .item() every step" if args.e2e_blocking else
                        "async copy to pinned memory every step, consumed two steps later; drained inside the timed region"}
 
@@ -1084,6 +1170,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="kitti-375x1242-1M", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-staging", default="ring", choices=["ring", "alloc"],
+                    help="device staging of the per-step inputs: ring of preallocated buffers, or a fresh tensor per step")
+    ap.add_argument("--e2e-ablate", default="none", choices=["none", "cot", "cam", "metric"],
+                    help="diagnosis: leave one per-step transfer out of the e2e loop (the line is then not a valid e2e)")
+    ap.add_argument("--sync-free-outstanding", type=int, default=None,
+                    help="sync-free forwards the host may run ahead of the device (GaussianModel.sync_free_outstanding)")
     ap.add_argument("--no-other-workloads", action="store_true",
                     help="skip the short runs of the other BASELINE configs (waymo 3-camera, stress 10M) at N=1")
     ap.add_argument("--launch-blocking-child", action="store_true", help=argparse.SUPPRESS)
