@@ -256,6 +256,65 @@ def make_cotangents(wl, device, seed=7, pinned=False):
     return {k: v.to(device) for k, v in host.items()}
 
 
+class InputStager:
+    """Device-side staging of the per-step inputs of the e2e loop: a ring of preallocated device buffers, refilled every
+    step from pinned host memory on a copy stream.
+
+    A fresh device tensor per step -- `host.to(device)` on the copy stream -- works too (`ring=False`), but its block
+    comes from the caching allocator's copy-stream pool, which grows by one cudaMalloc whenever the host gets one more
+    step ahead than it had been before; a cudaMalloc costs ~14 ms on these boxes, i.e. +0.14 ms/step over a 100-step
+    run for every one that lands inside it (profiles/r2_ab_e2e_ablation.txt).
+
+    A slot is refilled only after the kernels that read it have finished: the copy stream waits for the event its last
+    reader recorded (`release`), the host never does. `cuda` is torch.cuda (the CPU test passes a stand-in)."""
+
+    def __init__(self, host_tensors, device, copy_stream, ring=True, slots=4, cuda=None):
+        import torch
+        self.cuda = cuda if cuda is not None else torch.cuda
+        self.host = list(host_tensors)
+        self.device, self.copy_stream, self.ring, self.slots = device, copy_stream, ring, slots
+        self.buffers = [[torch.empty(h.shape, dtype=h.dtype, device=device) for h in self.host]
+                        for _ in range(slots)] if ring else []
+        self.slot_free = [None] * slots
+        self.staged = 0
+
+    def stage(self, skip=()):
+        """Queue this step's copies, in the order of `host_tensors` (small camera block first: a tiny copy issued behind
+        the 16.7 MB one would wait for it on the host-to-device copy engine and stall the forward).
+        -> (slot, [device tensor or None for indices in `skip`], [event recorded behind each copy])."""
+        k = self.staged % self.slots
+        self.staged += 1
+        out, events = [], []
+        with self.cuda.stream(self.copy_stream):
+            if self.ring and self.slot_free[k] is not None:
+                self.copy_stream.wait_event(self.slot_free[k])
+            for i, h in enumerate(self.host):
+                if i in skip:
+                    d = None
+                elif self.ring:
+                    d = self.buffers[k][i]
+                    d.copy_(h, non_blocking=True)
+                else:
+                    d = h.to(self.device, non_blocking=True)
+                ev = self.cuda.Event()
+                ev.record(self.copy_stream)
+                out.append(d)
+                events.append(ev)
+        return k, out, events
+
+    def reads_on_current_stream(self, t):
+        """Per-step tensors (ring=False): tell the allocator that the compute stream reads them."""
+        if not self.ring and t is not None:
+            t.record_stream(self.cuda.current_stream(self.device))
+
+    def release(self, k):
+        """Everything queued on the compute stream so far may read slot k."""
+        if self.ring:
+            ev = self.cuda.Event()
+            ev.record(self.cuda.current_stream(self.device))
+            self.slot_free[k] = ev
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -476,56 +535,17 @@ def run_ours(args):
     except Exception as exc:   # the probe must never take the bench line down with it
         sys.stderr.write(f"h2d probe failed: {exc}\n")
 
-    # Device-side staging of the per-step inputs: a ring of preallocated buffers, refilled every step from pinned
-    # memory on the copy stream. (A fresh device tensor per step -- `host_cot.to(device)` -- works too, but its block
-    # comes from the caching allocator's copy-stream pool, which grows by one cudaMalloc whenever the host gets one
-    # more step ahead than it had been before; a cudaMalloc costs ~14 ms on these boxes, i.e. +0.14 ms/step over a
-    # 100-step run for every one that lands inside it: profiles/r2_ab_e2e_ablation.txt. --e2e-staging alloc keeps
-    # that behaviour for comparison.) A slot is refilled only after the kernels that read it have finished: the copy
-    # stream waits for the event its last reader recorded, the host never does.
-    ring_n = 4
-    use_ring = args.e2e_staging == "ring"
-    cot_ring = [torch.empty(host_cot.shape, dtype=torch.float32, device=device) for _ in range(ring_n)] if use_ring else []
-    cam_ring = [torch.empty(host_cam.shape, dtype=torch.float32, device=device) for _ in range(ring_n)] if use_ring else []
-    slot_free = [None] * ring_n
-    staged = [0]
+    # per-step inputs: camera block first, cotangent planes behind it, through the copy stream (InputStager above);
+    # --e2e-staging alloc keeps the fresh-tensor-per-step behaviour for comparison
+    stager = InputStager([host_cam, host_cot], device, copy_stream, ring=(args.e2e_staging == "ring"))
 
     def stage_inputs():
-        """-> (slot, camera on the device, its event, cotangents on the device, their event); both copies go through
-        the copy stream, camera first: a tiny camera copy issued on the compute stream would queue behind the
-        16.7 MB transfer on the host-to-device copy engine and stall the forward."""
-        k = staged[0] % ring_n
-        staged[0] += 1
-        with torch.cuda.stream(copy_stream):
-            if use_ring:
-                if slot_free[k] is not None:
-                    copy_stream.wait_event(slot_free[k])
-                dcam = cam_ring[k]
-                dcam.copy_(host_cam, non_blocking=True)
-            else:
-                dcam = host_cam.to(device, non_blocking=True)
-            cam_ready = torch.cuda.Event()
-            cam_ready.record(copy_stream)
-            if args.e2e_ablate == "cot":
-                flat = static_flat
-            elif use_ring:
-                flat = cot_ring[k]
-                flat.copy_(host_cot, non_blocking=True)
-            else:
-                flat = host_cot.to(device, non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(copy_stream)
-        return k, dcam, cam_ready, flat, ready
+        """-> (slot, camera on the device, its event, cotangents on the device, their event)"""
+        k, (dcam, flat), (cam_ready, ready) = stager.stage(skip=(1,) if args.e2e_ablate == "cot" else ())
+        return k, dcam, cam_ready, (static_flat if flat is None else flat), ready
 
-    def use_on_compute_stream(t):
-        if not use_ring:        # per-step tensors: tell the allocator that the compute stream reads them
-            t.record_stream(torch.cuda.current_stream(device))
-
-    def release_inputs(k):
-        if use_ring:            # everything queued on the compute stream so far may read slot k
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(device))
-            slot_free[k] = ev
+    use_on_compute_stream = stager.reads_on_current_stream
+    release_inputs = stager.release
 
     # device -> host read of the step's metric: an asynchronous copy into pinned memory that the host
     # consumes two steps later (after the next two steps have been queued), the way a training loop logs its
@@ -647,7 +667,7 @@ def run_ours(args):
            # python + ctypes + launch time per step with the waits on the GPU taken out: when it approaches
            # ms_per_step the loop is bound by the host, not by the device
            "host_enqueue_ms_per_step": round(host_ms, 4),
-           "staging": ("ring of 4 preallocated device buffers refilled from pinned memory every step" if use_ring
+           "staging": ("ring of 4 preallocated device buffers refilled from pinned memory every step" if stager.ring
                        else "fresh device tensor per step"),
            "h2d_alone": None if not h2d_ms else {
                "ms_per_step": round(h2d_ms, 4), "GBps": round(host_cot.numel() * 4 / (h2d_ms * 1e-3) / 1e9, 2),

@@ -52,3 +52,99 @@ def test_elementwise_metric_catches_what_the_max_norm_hides():
     frac, worst = Hh.elementwise_err(a, b, rtol=1e-4, atol_frac=1e-6)
     assert abs(frac - 1 / 3) < 1e-12 and worst > 500   # ... but one element in three is off by ~900x its bound
     assert Hh.elementwise_err(b, b)[0] == 0.0
+
+
+class _FakeCuda:
+    """Stand-in for torch.cuda that records what bench.InputStager asks of it (tensors live on the CPU)."""
+
+    def __init__(self):
+        self.log = []
+        self.current = "compute"
+        outer = self
+
+        class Event:
+            def __init__(self):
+                self.recorded_on = None
+
+            def record(self, stream=None):
+                self.recorded_on = getattr(stream, "name", stream)
+                outer.log.append(("record", self.recorded_on))
+
+        class StreamCtx:
+            def __init__(self, stream):
+                self.stream = stream
+
+            def __enter__(self):
+                self.prev, outer.current = outer.current, self.stream.name
+
+            def __exit__(self, *exc):
+                outer.current = self.prev
+                return False
+
+        self.Event = Event
+        self._ctx = StreamCtx
+
+    def stream(self, s):
+        return self._ctx(s)
+
+    def current_stream(self, device=None):
+        return type("S", (), {"name": self.current})()
+
+
+class _FakeStream:
+    def __init__(self, name, cuda):
+        self.name, self.cuda = name, cuda
+
+    def wait_event(self, ev):
+        self.cuda.log.append(("wait", self.name, ev))
+
+
+def test_input_stager_rotates_preallocated_slots_and_orders_reuse_behind_the_reader():
+    import torch
+    cuda = _FakeCuda()
+    copy_stream = _FakeStream("copy", cuda)
+    cam, cot = torch.arange(35.0), torch.arange(1000.0)
+    st = bench.InputStager([cam, cot], "cpu", copy_stream, ring=True, slots=4, cuda=cuda)
+    assert len(st.buffers) == 4 and all(b[0].shape == cam.shape and b[1].shape == cot.shape for b in st.buffers)
+    ptrs = [(b[0].data_ptr(), b[1].data_ptr()) for b in st.buffers]
+    seen, releases = [], []
+    for step in range(9):
+        cam.fill_(float(step))           # this step's host data
+        cot.fill_(float(-step))
+        cuda.log.clear()
+        k, (dcam, dcot), (e_cam, e_cot) = st.stage()
+        assert k == step % 4 and (dcam.data_ptr(), dcot.data_ptr()) == ptrs[k]      # no allocation after __init__
+        assert torch.equal(dcam, cam) and torch.equal(dcot, cot)
+        assert e_cam.recorded_on == "copy" and e_cot.recorded_on == "copy"
+        waits = [x for x in cuda.log if x[0] == "wait"]
+        if step < 4:
+            assert waits == []                               # fresh slot: nothing to wait for
+        else:
+            # the copy stream waits for the event recorded on the COMPUTE stream when this slot's last reader was
+            # queued, before it overwrites the slot
+            assert len(waits) == 1 and waits[0][1] == "copy" and waits[0][2] is releases[step - 4]
+            assert cuda.log.index(waits[0]) == 0
+        assert cuda.current == "compute"                     # the stream context was left
+        st.release(k)
+        releases.append(st.slot_free[k])
+        assert releases[-1].recorded_on == "compute"
+        seen.append(k)
+    assert seen == [0, 1, 2, 3, 0, 1, 2, 3, 0]
+    # skipped input (diagnosis mode): no copy, but its event still exists
+    k, (dcam, dcot), evs = st.stage(skip=(1,))
+    assert dcot is None and dcam is not None and len(evs) == 2
+
+
+def test_input_stager_alloc_mode_makes_a_tensor_per_step_and_marks_its_reader():
+    import torch
+    cuda = _FakeCuda()
+    st = bench.InputStager([torch.ones(8)], "cpu", _FakeStream("copy", cuda), ring=False, cuda=cuda)
+    assert st.buffers == []
+    k, (d,), (ev,) = st.stage()
+    assert torch.equal(d, torch.ones(8)) and ev.recorded_on == "copy"
+    marked = []
+    d_proxy = type("T", (), {"record_stream": lambda self, s: marked.append(s.name)})()
+    st.reads_on_current_stream(d_proxy)
+    assert marked == ["compute"]
+    st.release(k)
+    assert st.slot_free[k] is None                       # nothing to order in this mode
